@@ -1,0 +1,209 @@
+/*
+ * rtx.h -- C ABI of the B200-native sequential geometric ray-trace engine.
+ *
+ * This is the drop-in boundary for ONE hot path of quartiq/rayopt: the
+ * per-surface  transfer -> intercept -> clip -> refract  loop
+ *
+ *     GeometricTrace.propagate      rayopt/geometric_trace.py:72-80
+ *       System.propagate            rayopt/system.py:459-464
+ *         TransformMixin.to_normal  rayopt/elements.py:174 (156-163)
+ *         Interface.propagate       rayopt/elements.py:306-315
+ *           Spheroid.intercept      rayopt/elements.py:477-501
+ *           Interface.intercept     rayopt/elements.py:333-349 (Newton, aspheres)
+ *           Element.clip            rayopt/elements.py:206-209
+ *           Interface.refract       rayopt/elements.py:351-369
+ *           Spheroid.surface_normal rayopt/elements.py:457-475
+ *           Spheroid.surface_sag    rayopt/elements.py:440-455
+ *         TransformMixin.from_normal rayopt/elements.py:171
+ *
+ * The reference has no FFI layer (pure numpy); the boundary it would bind is
+ * "one call per GeometricTrace.propagate()": a table of per-surface POD
+ * records (what System.propagate reads off each Element for one wavelength)
+ * plus the launch rays, returning the (S, N, 3) / (S, N) result arrays the
+ * reference stores into GeometricTrace.y/u/i/t (geometric_trace.py:80).
+ *
+ * Plain C, plain pointers and sizes.  No torch types.  Every function returns
+ * 0 on success, a NEGATIVE rtx error (RTX_E_*) for argument errors, or a
+ * POSITIVE cudaError_t for CUDA failures.  Numerical failure (missed surface,
+ * total internal reflection, vignetting, Newton non-convergence) is NOT an
+ * error: it is NaN in the data, exactly where the reference puts it
+ * (elements.py:208, 347-348, 367, 496).
+ *
+ * A context is bound to one GPU and one CUDA stream and is not thread-safe;
+ * use one context per GPU (one process per GPU in multi-GPU runs).
+ */
+#ifndef RTX_H
+#define RTX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTX_ABI_VERSION 1
+
+/* maximum number of even-asphere coefficients per surface (Spheroid.aspherics,
+ * elements.py:422-424).  Longer lists are rejected with RTX_E_UNSUPPORTED. */
+#define RTX_MAX_ASPH 10
+/* maximum number of surfaces in one trace call (bounded by the shared-memory
+ * staging of the surface table) */
+#define RTX_MAX_SURFACES 256
+
+/* rtx_surface.flags */
+#define RTX_F_ROTATED 1u /* apply rot (TransformMixin.rotated, elements.py:135) */
+#define RTX_F_ALT     2u /* Spheroid.alternate_intersection, elements.py:497-498 */
+
+/* dtype */
+#define RTX_F64 0
+#define RTX_F32 1
+
+/* keep policy */
+#define RTX_KEEP_ALL  0 /* store every surface: outputs have S rows   */
+#define RTX_KEEP_LAST 1 /* store only the last surface: outputs have 1 row */
+
+/* trace flags */
+#define RTX_EXACT      1u /* FP64 only: unfused IEEE arithmetic in numpy's
+                             evaluation order (bit-identical to the reference
+                             on unrotated analytic surfaces) */
+#define RTX_STORE_DIRECT 2u /* debug: force per-thread strided stores instead
+                               of the shared-memory staged bulk (TMA) stores */
+
+/* errors */
+#define RTX_OK              0
+#define RTX_E_BADARG       -1
+#define RTX_E_UNSUPPORTED  -2
+#define RTX_E_NOMEM        -3
+#define RTX_E_NCCL         -4
+
+/*
+ * One traced surface for one wavelength: everything System.propagate
+ * (system.py:459-464) and Interface.propagate (elements.py:306-315) read off
+ * the Element.  "Derived" members are scalars the reference computes in
+ * Python per call; a caller that wants bit-identical results must compute
+ * them with the same expressions (rayopt_b200/surface_table.py does);
+ * rtx_surface_finalize() fills them the C way.
+ */
+typedef struct rtx_surface {
+    double offset[3]; /* e.offset, subtracted in the incoming frame (system.py:461) */
+    double rot[9];    /* e.rot_normal, row-major; to_normal is y @ rot.T,
+                         from_normal is y @ rot (elements.py:156-175); used
+                         only if RTX_F_ROTATED */
+    double c;         /* Spheroid.curvature */
+    double k;         /* Spheroid.conic */
+    double kc2;       /* derived: (1 + k)*c**2          (elements.py:448,467) */
+    double radius2;   /* derived: radius**2, +inf = no aperture (elements.py:207) */
+    double mu;        /* 1 (no material), -1 (mirror) or n0/n (elements.py:283-289) */
+    double muf;       /* derived: abs(mu)               (elements.py:360) */
+    double sgn;       /* derived: sign(mu)              (elements.py:367) */
+    double mu2m1;     /* derived: mu**2 - 1             (elements.py:366) */
+    double n0;        /* index before the surface: t = s*n0 (elements.py:315) */
+    double n;         /* index after the surface (fills GeometricTrace.n) */
+    double asph[RTX_MAX_ASPH];  /* Spheroid.aspherics[j] multiplies r^(2(j+1)) */
+    double dasph[RTX_MAX_ASPH]; /* derived: 2*(j+1)*asph[j] (elements.py:472) */
+    int32_t n_asph;   /* -1: aspherics is None (analytic intercept);
+                         >=0: len(aspherics), Newton intercept even if 0
+                         (elements.py:478-479) */
+    uint32_t flags;   /* RTX_F_* */
+} rtx_surface;
+
+typedef struct rtx_ctx rtx_ctx;
+
+/* ---- library ---------------------------------------------------------- */
+int rtx_abi_version(void);
+/* number of CUDA devices visible, or 0 */
+int rtx_device_count(void);
+/* static string for an rtx (negative) or CUDA (positive) error code */
+const char *rtx_strerror(int code);
+/* fill the derived members of n records from c,k,mu,asph and `radius` */
+int rtx_surface_finalize(rtx_surface *surf, int n, const double *radius);
+
+/* ---- context ---------------------------------------------------------- */
+int rtx_init(int device, rtx_ctx **out);
+int rtx_free(rtx_ctx *ctx);
+int rtx_sync(rtx_ctx *ctx);
+/* device properties: SM count, and bytes of free / total HBM */
+int rtx_device_info(rtx_ctx *ctx, int *sm_count, size_t *free_bytes,
+                    size_t *total_bytes, char *name, int name_len);
+
+/* ---- memory (so that host code needs no other CUDA binding) ----------- */
+int rtx_malloc(rtx_ctx *ctx, size_t bytes, void **dptr);
+int rtx_free_device(rtx_ctx *ctx, void *dptr);
+int rtx_host_alloc(rtx_ctx *ctx, size_t bytes, void **hptr); /* pinned */
+int rtx_host_free(rtx_ctx *ctx, void *hptr);
+/* asynchronous on the context stream; rtx_sync() to complete */
+int rtx_memcpy_h2d(rtx_ctx *ctx, void *dst, const void *src, size_t bytes);
+int rtx_memcpy_d2h(rtx_ctx *ctx, void *dst, const void *src, size_t bytes);
+/* strided D2H: `height` rows of `width` bytes */
+int rtx_memcpy2d_d2h(rtx_ctx *ctx, void *dst, size_t dpitch, const void *src,
+                     size_t spitch, size_t width, size_t height);
+int rtx_memset(rtx_ctx *ctx, void *dptr, int value, size_t bytes);
+
+/* ---- timing on the context stream (CUDA events) ----------------------- */
+int rtx_timer_start(rtx_ctx *ctx);
+int rtx_timer_stop(rtx_ctx *ctx, float *ms); /* synchronises */
+/* device time of the most recent trace kernel launch(es) of the last
+ * rtx_trace call, measured with events around the launch */
+int rtx_last_kernel_ms(rtx_ctx *ctx, float *ms);
+/* number of kernels this context has launched so far */
+int64_t rtx_launch_count(rtx_ctx *ctx);
+
+/* ---- the hot path ------------------------------------------------------ */
+/*
+ * March N rays through S surfaces in one launch.  Replaces the loop
+ * GeometricTrace.propagate -> System.propagate (geometric_trace.py:72-80,
+ * system.py:459-464).
+ *
+ *  surf[S]  host pointer, surface records for system[start:stop]
+ *  rot0     host pointer to 9 doubles or NULL: rot_normal of system[start-1]
+ *           when that element is rotated; the launch rays are mapped with
+ *           from_normal (y @ rot0) first (geometric_trace.py:76)
+ *  dtype    RTX_F64 / RTX_F32: element type of ALL ray arrays
+ *  y0,u0    DEVICE pointers, (N,3) C-contiguous: launch rays in the normal
+ *           frame of system[start-1]
+ *  clip     0/1: the `clip` argument of propagate (elements.py:309-310)
+ *  keep     RTX_KEEP_ALL / RTX_KEEP_LAST
+ *  ld       row pitch of the outputs in RAYS (>= N).  Outputs are DEVICE
+ *           arrays Y,U,I: (rows, ld, 3), T: (rows, ld); rows = S or 1.
+ *           With ld a multiple of 64 rays the kernel uses staged bulk (TMA)
+ *           stores and writes whole 64-ray groups (columns N..ld-1 of the
+ *           last group are padding and receive unspecified values); any
+ *           other ld takes the per-thread store path and touches only
+ *           columns < N.
+ *           Y: intercepts, U: excidence, I: incidence directions (unclipped),
+ *           T: optical path s*n0 -- all in the surface-normal frame, exactly
+ *           the tuple System.propagate yields (system.py:463).
+ *           Any of Y,U,I,T may be NULL to skip storing that array.
+ */
+int rtx_trace(rtx_ctx *ctx, const rtx_surface *surf, int S,
+              const double *rot0, int dtype, int64_t N,
+              const void *y0, const void *u0, int clip, int keep, int64_t ld,
+              void *Y, void *U, void *I, void *T, unsigned flags);
+
+/*
+ * Same call with HOST buffers in the reference layout: y0,u0 (N,3);
+ * Y,U,I (rows,N,3), T (rows,N) C-contiguous (GeometricTrace.y/u/i/t rows
+ * start..stop-1).  Rays are processed in chunks; H2D, kernel and D2H of
+ * consecutive chunks overlap on three streams.  Host buffers from
+ * rtx_host_alloc (pinned) copy at full PCIe rate; pageable ones work too.
+ */
+int rtx_trace_host(rtx_ctx *ctx, const rtx_surface *surf, int S,
+                   const double *rot0, int dtype, int64_t N,
+                   const void *y0, const void *u0, int clip, int keep,
+                   void *Y, void *U, void *I, void *T, unsigned flags);
+
+/* ---- fused last-surface reductions (geometric_trace.py:171-183) ------- */
+/*
+ * Weighted moments of DEVICE intercepts y (N,3), dtype as given:
+ * m[0]=sum w, m[1]=sum w*x, m[2]=sum w*y, m[3]=sum w*(x^2+y^2),
+ * m[4]=count finite, m[5]=count total.  Rays with non-finite x or y are
+ * skipped (counted in m[5] only).  w may be NULL (w = 1).  m: host, 6 doubles.
+ */
+int rtx_moments(rtx_ctx *ctx, int dtype, int64_t N, const void *y,
+                const void *w, double *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTX_H */

@@ -1,0 +1,158 @@
+"""System -> rtx_surface[] packer (host side of the drop-in boundary).
+
+Walks a rayopt ``System`` (or anything that quacks like one: a sequence of
+elements with the attributes listed below) exactly the way
+``System.propagate`` (rayopt/system.py:459-464) and ``Interface.propagate``
+(rayopt/elements.py:306-315) do, and emits one POD record per traced surface
+for ONE wavelength.  ``System`` is mutable shared state (``refocus`` edits
+``system[at].distance``, rayopt/geometric_trace.py:98), so the table is
+re-packed on every ``propagate`` call; it is S small records.
+
+The "derived" members are computed here with the SAME Python expressions the
+reference evaluates per call (e.g. ``(1 + k)*c**2``, ``mu**2 - 1``), so that
+the engine's RTX_EXACT mode can be bit-identical to the reference.
+"""
+import numpy as np
+
+RTX_MAX_ASPH = 10
+RTX_MAX_SURFACES = 256
+F_ROTATED = 1
+F_ALT = 2
+
+# mirrors `struct rtx_surface` in include/rtx.h (natural C alignment; the size
+# is cross-checked against rtx_sizeof_surface() when the library is loaded)
+SURFACE_DTYPE = np.dtype([
+    ("offset", "<f8", (3,)),
+    ("rot", "<f8", (9,)),
+    ("c", "<f8"),
+    ("k", "<f8"),
+    ("kc2", "<f8"),
+    ("radius2", "<f8"),
+    ("mu", "<f8"),
+    ("muf", "<f8"),
+    ("sgn", "<f8"),
+    ("mu2m1", "<f8"),
+    ("n0", "<f8"),
+    ("n", "<f8"),
+    ("asph", "<f8", (RTX_MAX_ASPH,)),
+    ("dasph", "<f8", (RTX_MAX_ASPH,)),
+    ("n_asph", "<i4"),
+    ("flags", "<u4"),
+], align=True)
+
+
+def get_n_mu(element, n0, l):
+    """Interface.get_n_mu (rayopt/elements.py:283-289), duck-typed; a plain
+    ``Element`` has no material and never refracts (elements.py:230-236)."""
+    fn = getattr(element, "get_n_mu", None)
+    if fn is not None:
+        n, mu = fn(n0, l)
+        return n, mu
+    return n0, 1.
+
+
+def pack_element(rec, e, n0, l):
+    """Fill one record from element `e` hit from a medium of index `n0` at
+    wavelength `l`; returns the index after the surface."""
+    rec["offset"] = np.asarray(e.offset, float)            # system.py:461
+    flags = 0
+    if getattr(e, "rotated", False):                       # elements.py:135
+        flags |= F_ROTATED
+        rec["rot"] = np.asarray(e.rot_normal, float).reshape(9)
+    else:
+        rec["rot"] = np.eye(3).reshape(9)
+    c = getattr(e, "curvature", 0.)
+    k = getattr(e, "conic", 0.)
+    asph = getattr(e, "aspherics", None)
+    if getattr(e, "alternate_intersection", False):        # elements.py:497
+        flags |= F_ALT
+    rec["c"] = c
+    rec["k"] = k
+    rec["kc2"] = (1 + k)*c**2                              # elements.py:448,467
+    radius = getattr(e, "radius", np.inf)
+    rec["radius2"] = radius**2                             # elements.py:207
+    n, mu = get_n_mu(e, n0, l)
+    if not mu:                                             # elements.py:313
+        mu = 1.
+    rec["mu"] = mu
+    rec["muf"] = abs(mu)                                   # elements.py:360
+    rec["sgn"] = np.sign(mu)                               # elements.py:367
+    rec["mu2m1"] = mu**2 - 1                               # elements.py:366
+    rec["n0"] = n0
+    rec["n"] = n
+    rec["asph"] = 0.
+    rec["dasph"] = 0.
+    if asph is None:
+        rec["n_asph"] = -1                                 # elements.py:478
+    else:
+        asph = list(asph)
+        if len(asph) > RTX_MAX_ASPH:
+            raise ValueError("at most %d aspheric coefficients are supported, "
+                             "got %d" % (RTX_MAX_ASPH, len(asph)))
+        rec["n_asph"] = len(asph)
+        for i, a in enumerate(asph):
+            rec["asph"][i] = a
+            rec["dasph"][i] = 2*(i + 1)*a                  # elements.py:472
+    rec["flags"] = flags
+    return n
+
+
+def pack_system(system, l, start=1, stop=None, n0=None):
+    """Records for ``system[start:stop]`` at wavelength `l`.
+
+    `n0` is the index in front of ``system[start]``; default
+    ``system.refractive_index(l, start - 1)`` walked the way
+    ``GeometricTrace.rays_given`` does for start == 1
+    (rayopt/geometric_trace.py:69).
+
+    Returns ``(table, n, rot0)``: the structured array, the (S,) array of
+    indices after each surface (what the reference stores into
+    ``GeometricTrace.n[start:stop]``) and the 3x3 ``rot_normal`` of
+    ``system[start-1]`` or None (geometric_trace.py:76).
+    """
+    elements = list(system[start:stop])
+    if len(elements) > RTX_MAX_SURFACES:
+        raise ValueError("too many surfaces: %d" % len(elements))
+    if n0 is None:
+        n0 = system.refractive_index(l, start - 1)
+    table = np.zeros(len(elements), SURFACE_DTYPE)
+    n = np.empty(len(elements))
+    for j, e in enumerate(elements):
+        n0 = pack_element(table[j], e, n0, l)
+        n[j] = n0
+    init = system[start - 1]
+    rot0 = None
+    if getattr(init, "rotated", False):
+        rot0 = np.ascontiguousarray(init.rot_normal, float)
+    return table, n, rot0
+
+
+def table_to_json(table):
+    """Lossless (repr-exact floats) JSON-able form of a table."""
+    out = []
+    for rec in table:
+        d = {}
+        for name in SURFACE_DTYPE.names:
+            v = rec[name]
+            if isinstance(v, np.ndarray):
+                d[name] = [float(x).hex() for x in v]
+            elif name in ("n_asph", "flags"):
+                d[name] = int(v)
+            else:
+                d[name] = float(v).hex()
+        out.append(d)
+    return out
+
+
+def table_from_json(items):
+    table = np.zeros(len(items), SURFACE_DTYPE)
+    for rec, d in zip(table, items):
+        for name in SURFACE_DTYPE.names:
+            v = d[name]
+            if isinstance(v, list):
+                rec[name] = [float.fromhex(x) for x in v]
+            elif name in ("n_asph", "flags"):
+                rec[name] = v
+            else:
+                rec[name] = float.fromhex(v)
+    return table
