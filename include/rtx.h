@@ -112,6 +112,8 @@ typedef struct rtx_ctx rtx_ctx;
 
 /* ---- library ---------------------------------------------------------- */
 int rtx_abi_version(void);
+/* sizeof(rtx_surface) as compiled, for binding-side layout checks */
+size_t rtx_sizeof_surface(void);
 /* number of CUDA devices visible, or 0 */
 int rtx_device_count(void);
 /* static string for an rtx (negative) or CUDA (positive) error code */

@@ -1,0 +1,599 @@
+// rtx.cu -- C ABI of the ray-trace engine (include/rtx.h): context, memory,
+// the table conversion and the kernel launches.  Build:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared \
+//        -Xcompiler -fPIC -o librtx.so rtx.cu
+#include "../../include/rtx.h"
+#include "rtx_device.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace rtx;
+
+#define CK(call)                                \
+    do {                                        \
+        cudaError_t e_ = (call);                \
+        if (e_ != cudaSuccess) return (int)e_;  \
+    } while (0)
+
+namespace {
+
+constexpr int TABLE_SLOTS = 8;
+
+struct TableSlot {
+    void* host = nullptr;  // pinned
+    void* dev = nullptr;
+    cudaEvent_t done = nullptr;
+    bool used = false;
+};
+
+struct ChunkBuf {
+    void* y0 = nullptr;
+    void* u0 = nullptr;
+    void* Y = nullptr;
+    void* U = nullptr;
+    void* I = nullptr;
+    void* T = nullptr;
+    size_t in_bytes = 0, out3_bytes = 0, out1_bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+
+}  // namespace
+
+struct rtx_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;    // rtx_timer_*
+    cudaEvent_t k0 = nullptr, k1 = nullptr;    // around the last trace launch
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> chunk_events;
+    bool kernel_timed = false;
+    TableSlot slots[TABLE_SLOTS];
+    int next_slot = 0;
+    size_t slot_bytes = 0;
+    ChunkBuf chunk[2];
+    double* d_moments = nullptr;
+    int64_t launches = 0;
+    int max_smem_optin = 0;
+};
+
+namespace {
+
+template <typename T>
+void convert_surface(const rtx_surface& s, DevSurf<T>& d) {
+    memset(&d, 0, sizeof(d));
+    for (int i = 0; i < 3; ++i) d.off[i] = (T)s.offset[i];
+    for (int i = 0; i < 9; ++i) d.rot[i] = (T)s.rot[i];
+    d.c = (T)s.c;
+    d.k1 = (T)(1.0 + s.k);
+    d.kc2 = (T)s.kc2;
+    d.radius2 = (T)s.radius2;
+    d.mu = (T)s.mu;
+    d.muf = (T)s.muf;
+    d.sgn = (T)s.sgn;
+    d.mu2m1 = (T)s.mu2m1;
+    d.n0 = (T)s.n0;
+    d.inv_c = s.c != 0.0 ? (T)(1.0 / s.c) : (T)0;
+    d.kc2k = (T)(s.k * s.c * s.c);
+    for (int i = 0; i < RTX_MAX_ASPH; ++i) {
+        d.asph[i] = (T)s.asph[i];
+        d.dasph[i] = (T)s.dasph[i];
+    }
+    d.n_asph = s.n_asph;
+    unsigned f = 0;
+    if (s.flags & RTX_F_ROTATED) f |= DF_ROTATED;
+    if (s.flags & RTX_F_ALT) f |= DF_ALT;
+    if (s.c == 0.0 && s.n_asph < 0) f |= DF_FLATNORMAL;
+    if (s.c != 0.0) f |= DF_CURVED;
+    d.flags = f;
+    // branch selection of Spheroid.intercept, elements.py:478-488
+    if (s.n_asph >= 0)
+        d.kind = KIND_NEWTON;
+    else if (s.c == 0.0)
+        d.kind = KIND_PLANE;
+    else if (s.k == 0.0)
+        d.kind = KIND_SPHERE;
+    else
+        d.kind = KIND_CONIC;
+    // Interface.refract, elements.py:356,363
+    if (s.mu == 1.0)
+        d.refr = REFR_NONE;
+    else if (s.mu == -1.0)
+        d.refr = REFR_MIRROR;
+    else
+        d.refr = REFR_SNELL;
+}
+
+int ensure_slots(rtx_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->slot_bytes) return 0;
+    size_t nb = bytes < 16384 ? 16384 : bytes;
+    for (auto& sl : ctx->slots) {
+        if (sl.used) CK(cudaEventSynchronize(sl.done));
+        if (sl.host) CK(cudaFreeHost(sl.host));
+        if (sl.dev) CK(cudaFree(sl.dev));
+        sl.host = sl.dev = nullptr;
+        CK(cudaMallocHost(&sl.host, nb));
+        CK(cudaMalloc(&sl.dev, nb));
+        if (!sl.done) CK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        sl.used = false;
+    }
+    ctx->slot_bytes = nb;
+    return 0;
+}
+
+template <typename T, bool EXACT, bool BULK>
+int launch_one(rtx_ctx* ctx, const TraceParams<T>& p, cudaStream_t stream) {
+    auto kern = trace_kernel<T, EXACT, BULK>;
+    size_t smem = trace_smem_bytes<T>(p.S, BULK);
+    if ((int)smem > ctx->max_smem_optin) return RTX_E_UNSUPPORTED;
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+    if (occ < 1) occ = 1;
+    long long tiles = (p.N + THREADS - 1) / THREADS;
+    long long grid = (long long)ctx->sm_count * occ;
+    if (grid > tiles) grid = tiles;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, THREADS, smem, stream>>>(p);
+    ctx->launches++;
+    return (int)cudaGetLastError();
+}
+
+template <typename T>
+int launch_trace(rtx_ctx* ctx, const TraceParams<T>& p, bool exact, bool bulk,
+                 cudaStream_t stream);
+
+template <>
+int launch_trace<double>(rtx_ctx* ctx, const TraceParams<double>& p, bool exact, bool bulk,
+                         cudaStream_t stream) {
+    if (exact)
+        return bulk ? launch_one<double, true, true>(ctx, p, stream)
+                    : launch_one<double, true, false>(ctx, p, stream);
+    return bulk ? launch_one<double, false, true>(ctx, p, stream)
+                : launch_one<double, false, false>(ctx, p, stream);
+}
+template <>
+int launch_trace<float>(rtx_ctx* ctx, const TraceParams<float>& p, bool exact, bool bulk,
+                        cudaStream_t stream) {
+    if (exact) return RTX_E_UNSUPPORTED;  // RTX_EXACT is FP64 only
+    return bulk ? launch_one<float, false, true>(ctx, p, stream)
+                : launch_one<float, false, false>(ctx, p, stream);
+}
+
+// convert + upload the table; returns the device pointer.  The copy is
+// ordered on `stream`; the pinned slot is recycled only after its copy ran.
+template <typename T>
+int upload_table(rtx_ctx* ctx, const rtx_surface* surf, int S, cudaStream_t stream,
+                 const DevSurf<T>** out) {
+    size_t bytes = (size_t)S * sizeof(DevSurf<T>);
+    int rc = ensure_slots(ctx, bytes);
+    if (rc) return rc;
+    TableSlot& sl = ctx->slots[ctx->next_slot];
+    ctx->next_slot = (ctx->next_slot + 1) % TABLE_SLOTS;
+    if (sl.used) CK(cudaEventSynchronize(sl.done));
+    DevSurf<T>* h = reinterpret_cast<DevSurf<T>*>(sl.host);
+    for (int i = 0; i < S; ++i) convert_surface<T>(surf[i], h[i]);
+    CK(cudaMemcpyAsync(sl.dev, sl.host, bytes, cudaMemcpyHostToDevice, stream));
+    CK(cudaEventRecord(sl.done, stream));
+    sl.used = true;
+    *out = reinterpret_cast<const DevSurf<T>*>(sl.dev);
+    return 0;
+}
+
+int check_table(const rtx_surface* surf, int S) {
+    if (!surf || S < 1 || S > RTX_MAX_SURFACES) return RTX_E_BADARG;
+    for (int i = 0; i < S; ++i) {
+        if (surf[i].n_asph > RTX_MAX_ASPH) return RTX_E_UNSUPPORTED;
+        if (surf[i].n_asph < -1) return RTX_E_BADARG;
+    }
+    return 0;
+}
+
+template <typename T>
+int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0, long long N,
+                 const void* y0, const void* u0, int clip, int keep, long long ld, void* Y,
+                 void* U, void* I, void* Tt, unsigned flags, cudaStream_t stream,
+                 const DevSurf<T>* table /* may be null: upload */) {
+    if (!table) {
+        int rc = upload_table<T>(ctx, surf, S, stream, &table);
+        if (rc) return rc;
+    }
+    TraceParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.table = table;
+    p.S = S;
+    p.clip = clip ? 1 : 0;
+    p.keep_last = keep == RTX_KEEP_LAST;
+    p.has_rot0 = rot0 != nullptr;
+    if (rot0)
+        for (int i = 0; i < 9; ++i) p.rot0[i] = (T)rot0[i];
+    p.N = N;
+    p.ld = ld;
+    p.y0 = (const T*)y0;
+    p.u0 = (const T*)u0;
+    p.Y = (T*)Y;
+    p.U = (T*)U;
+    p.I = (T*)I;
+    p.Tt = (T*)Tt;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    bool bulk = !(flags & RTX_STORE_DIRECT) && (ld % 32 == 0) && al16(Y) && al16(U) && al16(I) &&
+                al16(Tt);
+    return launch_trace<T>(ctx, p, (flags & RTX_EXACT) != 0, bulk, stream);
+}
+
+int ensure_chunk(rtx_ctx* ctx, ChunkBuf& cb, size_t in_bytes, size_t out3, size_t out1) {
+    if (!cb.stream) CK(cudaStreamCreateWithFlags(&cb.stream, cudaStreamNonBlocking));
+    if (in_bytes > cb.in_bytes) {
+        if (cb.y0) CK(cudaFree(cb.y0));
+        if (cb.u0) CK(cudaFree(cb.u0));
+        cb.y0 = cb.u0 = nullptr;
+        cb.in_bytes = 0;
+        CK(cudaMalloc(&cb.y0, in_bytes));
+        CK(cudaMalloc(&cb.u0, in_bytes));
+        cb.in_bytes = in_bytes;
+    }
+    if (out3 > cb.out3_bytes) {
+        if (cb.Y) CK(cudaFree(cb.Y));
+        if (cb.U) CK(cudaFree(cb.U));
+        if (cb.I) CK(cudaFree(cb.I));
+        cb.Y = cb.U = cb.I = nullptr;
+        cb.out3_bytes = 0;
+        CK(cudaMalloc(&cb.Y, out3));
+        CK(cudaMalloc(&cb.U, out3));
+        CK(cudaMalloc(&cb.I, out3));
+        cb.out3_bytes = out3;
+    }
+    if (out1 > cb.out1_bytes) {
+        if (cb.T) CK(cudaFree(cb.T));
+        cb.T = nullptr;
+        cb.out1_bytes = 0;
+        CK(cudaMalloc(&cb.T, out1));
+        cb.out1_bytes = out1;
+    }
+    return 0;
+}
+
+void free_chunk(ChunkBuf& cb) {
+    if (cb.y0) cudaFree(cb.y0);
+    if (cb.u0) cudaFree(cb.u0);
+    if (cb.Y) cudaFree(cb.Y);
+    if (cb.U) cudaFree(cb.U);
+    if (cb.I) cudaFree(cb.I);
+    if (cb.T) cudaFree(cb.T);
+    if (cb.stream) cudaStreamDestroy(cb.stream);
+    cb = ChunkBuf();
+}
+
+void clear_chunk_events(rtx_ctx* ctx) {
+    for (auto& pr : ctx->chunk_events) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    ctx->chunk_events.clear();
+}
+
+template <typename T>
+int trace_host(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0, long long N,
+               const void* y0, const void* u0, int clip, int keep, void* Y, void* U, void* I,
+               void* Tt, unsigned flags) {
+    const int rows = keep == RTX_KEEP_LAST ? 1 : S;
+    // chunk: ~256 MB of results, whole 64-ray groups
+    long long per_ray = (long long)rows * 10 * sizeof(T) + 6 * sizeof(T);
+    long long C = (256ll << 20) / per_ray;
+    C = (C / 64) * 64;
+    if (C < 4096) C = 4096;
+    if (C > N) C = ((N + 63) / 64) * 64;
+    const size_t in_bytes = (size_t)C * 3 * sizeof(T);
+    const size_t out3 = (size_t)rows * C * 3 * sizeof(T);
+    const size_t out1 = (size_t)rows * C * sizeof(T);
+    for (int b = 0; b < 2; ++b) {
+        int rc = ensure_chunk(ctx, ctx->chunk[b], in_bytes, out3, out1);
+        if (rc) return rc;
+    }
+    // the table is uploaded once on the main stream; chunk streams wait for it
+    const DevSurf<T>* table = nullptr;
+    int rc = upload_table<T>(ctx, surf, S, ctx->stream, &table);
+    if (rc) return rc;
+    cudaEvent_t table_ready;
+    CK(cudaEventCreateWithFlags(&table_ready, cudaEventDisableTiming));
+    CK(cudaEventRecord(table_ready, ctx->stream));
+    clear_chunk_events(ctx);
+    int nchunk = 0;
+    for (long long c0 = 0; c0 < N; c0 += C, ++nchunk) {
+        ChunkBuf& cb = ctx->chunk[nchunk & 1];
+        const long long n = (N - c0 < C) ? (N - c0) : C;
+        if (nchunk < 2) CK(cudaStreamWaitEvent(cb.stream, table_ready, 0));
+        CK(cudaMemcpyAsync(cb.y0, (const T*)y0 + c0 * 3, (size_t)n * 3 * sizeof(T),
+                           cudaMemcpyHostToDevice, cb.stream));
+        CK(cudaMemcpyAsync(cb.u0, (const T*)u0 + c0 * 3, (size_t)n * 3 * sizeof(T),
+                           cudaMemcpyHostToDevice, cb.stream));
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        ctx->chunk_events.emplace_back(e0, e1);
+        CK(cudaEventRecord(e0, cb.stream));
+        rc = trace_device<T>(ctx, surf, S, rot0, n, cb.y0, cb.u0, clip, keep, C, Y ? cb.Y : nullptr,
+                             U ? cb.U : nullptr, I ? cb.I : nullptr, Tt ? cb.T : nullptr, flags,
+                             cb.stream, table);
+        if (rc) return rc;
+        CK(cudaEventRecord(e1, cb.stream));
+        const size_t w3 = (size_t)n * 3 * sizeof(T), w1 = (size_t)n * sizeof(T);
+        const size_t sp3 = (size_t)C * 3 * sizeof(T), sp1 = (size_t)C * sizeof(T);
+        const size_t dp3 = (size_t)N * 3 * sizeof(T), dp1 = (size_t)N * sizeof(T);
+        if (Y)
+            CK(cudaMemcpy2DAsync((T*)Y + c0 * 3, dp3, cb.Y, sp3, w3, rows, cudaMemcpyDeviceToHost,
+                                 cb.stream));
+        if (U)
+            CK(cudaMemcpy2DAsync((T*)U + c0 * 3, dp3, cb.U, sp3, w3, rows, cudaMemcpyDeviceToHost,
+                                 cb.stream));
+        if (I)
+            CK(cudaMemcpy2DAsync((T*)I + c0 * 3, dp3, cb.I, sp3, w3, rows, cudaMemcpyDeviceToHost,
+                                 cb.stream));
+        if (Tt)
+            CK(cudaMemcpy2DAsync((T*)Tt + c0, dp1, cb.T, sp1, w1, rows, cudaMemcpyDeviceToHost,
+                                 cb.stream));
+    }
+    for (int b = 0; b < 2; ++b) CK(cudaStreamSynchronize(ctx->chunk[b].stream));
+    CK(cudaEventDestroy(table_ready));
+    ctx->kernel_timed = false;
+    return 0;
+}
+
+}  // namespace
+
+// =========================================================================
+extern "C" {
+
+int rtx_abi_version(void) { return RTX_ABI_VERSION; }
+
+size_t rtx_sizeof_surface(void) { return sizeof(rtx_surface); }
+
+int rtx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* rtx_strerror(int code) {
+    switch (code) {
+        case RTX_OK: return "ok";
+        case RTX_E_BADARG: return "rtx: bad argument";
+        case RTX_E_UNSUPPORTED: return "rtx: unsupported (too many aspheric coefficients / surfaces, or RTX_EXACT with FP32)";
+        case RTX_E_NOMEM: return "rtx: out of memory";
+        case RTX_E_NCCL: return "rtx: NCCL error";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "rtx: unknown error";
+}
+
+int rtx_surface_finalize(rtx_surface* surf, int n, const double* radius) {
+    if (!surf || n < 0) return RTX_E_BADARG;
+    for (int i = 0; i < n; ++i) {
+        rtx_surface& s = surf[i];
+        s.kc2 = (1.0 + s.k) * (s.c * s.c);
+        if (radius) s.radius2 = radius[i] * radius[i];
+        s.muf = fabs(s.mu);
+        s.sgn = s.mu > 0 ? 1.0 : (s.mu < 0 ? -1.0 : 0.0);
+        s.mu2m1 = s.mu * s.mu - 1.0;
+        for (int j = 0; j < RTX_MAX_ASPH; ++j)
+            s.dasph[j] = (j < s.n_asph) ? (double)(2 * (j + 1)) * s.asph[j] : 0.0;
+    }
+    return 0;
+}
+
+int rtx_init(int device, rtx_ctx** out) {
+    if (!out) return RTX_E_BADARG;
+    int n = 0;
+    CK(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return RTX_E_BADARG;
+    CK(cudaSetDevice(device));
+    rtx_ctx* ctx = new (std::nothrow) rtx_ctx();
+    if (!ctx) return RTX_E_NOMEM;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ctx->t0));
+    CK(cudaEventCreate(&ctx->t1));
+    CK(cudaEventCreate(&ctx->k0));
+    CK(cudaEventCreate(&ctx->k1));
+    CK(cudaMalloc((void**)&ctx->d_moments, 6 * sizeof(double)));
+    *out = ctx;
+    return 0;
+}
+
+int rtx_free(rtx_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    clear_chunk_events(ctx);
+    for (auto& sl : ctx->slots) {
+        if (sl.host) cudaFreeHost(sl.host);
+        if (sl.dev) cudaFree(sl.dev);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    free_chunk(ctx->chunk[0]);
+    free_chunk(ctx->chunk[1]);
+    if (ctx->d_moments) cudaFree(ctx->d_moments);
+    cudaEventDestroy(ctx->t0);
+    cudaEventDestroy(ctx->t1);
+    cudaEventDestroy(ctx->k0);
+    cudaEventDestroy(ctx->k1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+int rtx_sync(rtx_ctx* ctx) {
+    if (!ctx) return RTX_E_BADARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int rtx_device_info(rtx_ctx* ctx, int* sm_count, size_t* free_bytes, size_t* total_bytes,
+                    char* name, int name_len) {
+    if (!ctx) return RTX_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    if (sm_count) *sm_count = ctx->sm_count;
+    size_t f = 0, t = 0;
+    CK(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    if (name && name_len > 0) {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, ctx->device));
+        snprintf(name, (size_t)name_len, "%s", prop.name);
+    }
+    return 0;
+}
+
+int rtx_malloc(rtx_ctx* ctx, size_t bytes, void** dptr) {
+    if (!ctx || !dptr) return RTX_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMalloc(dptr, bytes ? bytes : 16));
+    return 0;
+}
+int rtx_free_device(rtx_ctx* ctx, void* dptr) {
+    if (!ctx) return RTX_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaFree(dptr));
+    return 0;
+}
+int rtx_host_alloc(rtx_ctx* ctx, size_t bytes, void** hptr) {
+    if (!ctx || !hptr) return RTX_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMallocHost(hptr, bytes ? bytes : 16));
+    return 0;
+}
+int rtx_host_free(rtx_ctx* ctx, void* hptr) {
+    if (!ctx) return RTX_E_BADARG;
+    CK(cudaFreeHost(hptr));
+    return 0;
+}
+int rtx_memcpy_h2d(rtx_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return RTX_E_BADARG;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+int rtx_memcpy_d2h(rtx_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return RTX_E_BADARG;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+int rtx_memcpy2d_d2h(rtx_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch,
+                     size_t width, size_t height) {
+    if (!ctx) return RTX_E_BADARG;
+    CK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost,
+                         ctx->stream));
+    return 0;
+}
+int rtx_memset(rtx_ctx* ctx, void* dptr, int value, size_t bytes) {
+    if (!ctx) return RTX_E_BADARG;
+    CK(cudaMemsetAsync(dptr, value, bytes, ctx->stream));
+    return 0;
+}
+
+int rtx_timer_start(rtx_ctx* ctx) {
+    if (!ctx) return RTX_E_BADARG;
+    CK(cudaEventRecord(ctx->t0, ctx->stream));
+    return 0;
+}
+int rtx_timer_stop(rtx_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return RTX_E_BADARG;
+    CK(cudaEventRecord(ctx->t1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->t1));
+    CK(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return 0;
+}
+int rtx_last_kernel_ms(rtx_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return RTX_E_BADARG;
+    if (ctx->kernel_timed) {
+        CK(cudaEventSynchronize(ctx->k1));
+        CK(cudaEventElapsedTime(ms, ctx->k0, ctx->k1));
+        return 0;
+    }
+    float tot = 0.f;
+    for (auto& pr : ctx->chunk_events) {
+        float t = 0.f;
+        CK(cudaEventSynchronize(pr.second));
+        CK(cudaEventElapsedTime(&t, pr.first, pr.second));
+        tot += t;
+    }
+    *ms = tot;
+    return 0;
+}
+int64_t rtx_launch_count(rtx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int rtx_trace(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0, int dtype,
+              int64_t N, const void* y0, const void* u0, int clip, int keep, int64_t ld, void* Y,
+              void* U, void* I, void* T, unsigned flags) {
+    if (!ctx) return RTX_E_BADARG;
+    int rc = check_table(surf, S);
+    if (rc) return rc;
+    if (N < 0 || ld < N || !y0 || !u0) return RTX_E_BADARG;
+    if (keep != RTX_KEEP_ALL && keep != RTX_KEEP_LAST) return RTX_E_BADARG;
+    if (dtype != RTX_F64 && dtype != RTX_F32) return RTX_E_BADARG;
+    if (N == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->k0, ctx->stream));
+    if (dtype == RTX_F64)
+        rc = trace_device<double>(ctx, surf, S, rot0, N, y0, u0, clip, keep, ld, Y, U, I, T, flags,
+                                  ctx->stream, nullptr);
+    else
+        rc = trace_device<float>(ctx, surf, S, rot0, N, y0, u0, clip, keep, ld, Y, U, I, T, flags,
+                                 ctx->stream, nullptr);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->k1, ctx->stream));
+    ctx->kernel_timed = true;
+    return 0;
+}
+
+int rtx_trace_host(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0, int dtype,
+                   int64_t N, const void* y0, const void* u0, int clip, int keep, void* Y, void* U,
+                   void* I, void* T, unsigned flags) {
+    if (!ctx) return RTX_E_BADARG;
+    int rc = check_table(surf, S);
+    if (rc) return rc;
+    if (N < 0 || !y0 || !u0) return RTX_E_BADARG;
+    if (keep != RTX_KEEP_ALL && keep != RTX_KEEP_LAST) return RTX_E_BADARG;
+    if (dtype != RTX_F64 && dtype != RTX_F32) return RTX_E_BADARG;
+    if (N == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    if (dtype == RTX_F64)
+        return trace_host<double>(ctx, surf, S, rot0, N, y0, u0, clip, keep, Y, U, I, T, flags);
+    return trace_host<float>(ctx, surf, S, rot0, N, y0, u0, clip, keep, Y, U, I, T, flags);
+}
+
+int rtx_moments(rtx_ctx* ctx, int dtype, int64_t N, const void* y, const void* w, double* m) {
+    if (!ctx || !y || !m || N < 0) return RTX_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_moments, 0, 6 * sizeof(double), ctx->stream));
+    if (N > 0) {
+        long long blocks = (N + 255) / 256;
+        long long cap = (long long)ctx->sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        if (dtype == RTX_F64)
+            moments_kernel<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+                (const double*)y, (const double*)w, N, ctx->d_moments);
+        else if (dtype == RTX_F32)
+            moments_kernel<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+                (const float*)y, (const float*)w, N, ctx->d_moments);
+        else
+            return RTX_E_BADARG;
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(m, ctx->d_moments, 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,240 @@
+"""Host-side handle of one GPU context of the ray-trace engine.
+
+Thin, torch-free layer over the C ABI (include/rtx.h): device / pinned memory,
+the trace call with host or device buffers, CUDA-event timing.  One `Engine`
+per GPU (one process per GPU in multi-GPU runs).
+"""
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib
+from ._lib import (RTX_F32, RTX_F64, RTX_KEEP_ALL, RTX_KEEP_LAST, RTX_EXACT,
+                   RTX_STORE_DIRECT, RtxError, check, ptr)
+from .surface_table import SURFACE_DTYPE
+
+_DTYPES = {np.dtype(np.float64): RTX_F64, np.dtype(np.float32): RTX_F32}
+
+
+def _code(dtype):
+    try:
+        return _DTYPES[np.dtype(dtype)]
+    except KeyError:
+        raise TypeError("dtype must be float64 or float32, got %r" % (dtype,))
+
+
+class DeviceArray:
+    """A typed block of HBM owned by an Engine (freed with it or on .free())."""
+
+    def __init__(self, engine, shape, dtype):
+        self.engine = engine
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64))*self.dtype.itemsize
+        p = C.c_void_p()
+        check(engine.lib.rtx_malloc(engine.ctx, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+        engine._live[id(self)] = self.ptr
+
+    def free(self):
+        if self.ptr is not None and self.engine.ctx is not None:
+            check(self.engine.lib.rtx_free_device(self.engine.ctx, self.ptr))
+            self.engine._live.pop(id(self), None)
+        self.ptr = None
+
+    def upload(self, a):
+        a = np.ascontiguousarray(a, self.dtype)
+        assert a.nbytes <= self.nbytes
+        check(self.engine.lib.rtx_memcpy_h2d(self.engine.ctx, self.ptr, ptr(a), a.nbytes))
+        self.engine.sync()          # `a` may be a temporary
+        return self
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty(self.shape, self.dtype)
+        check(self.engine.lib.rtx_memcpy_d2h(self.engine.ctx, ptr(out), self.ptr, out.nbytes))
+        self.engine.sync()
+        return out
+
+    def rows(self, r0, r1=None):
+        """byte-offset view of leading-axis rows (no copy)"""
+        v = object.__new__(DeviceArray)
+        r1 = r0 + 1 if r1 is None else r1
+        row_bytes = self.nbytes//self.shape[0]
+        v.engine, v.dtype = self.engine, self.dtype
+        v.shape = (r1 - r0,) + self.shape[1:]
+        v.nbytes = row_bytes*(r1 - r0)
+        v.ptr = self.ptr + r0*row_bytes
+        v.free = lambda: None
+        return v
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        self.ctx = None
+        if self.lib.rtx_device_count() < 1:
+            raise RtxError("no CUDA device visible: the rayopt_b200 engine has "
+                           "no CPU fallback")
+        ctx = C.c_void_p()
+        check(self.lib.rtx_init(int(device), C.byref(ctx)))
+        self.ctx = ctx
+        self.device = int(device)
+        self._live = {}
+        self._pinned = {}
+        sm, fr, tot = C.c_int(), C.c_size_t(), C.c_size_t()
+        name = C.create_string_buffer(128)
+        check(self.lib.rtx_device_info(self.ctx, C.byref(sm), C.byref(fr), C.byref(tot), name, 128))
+        self.sm_count, self.total_bytes = sm.value, tot.value
+        self.name = name.value.decode()
+        self._fin = weakref.finalize(self, Engine._finalize, self.lib, self.ctx)
+
+    @staticmethod
+    def _finalize(lib, ctx):
+        try:
+            lib.rtx_free(ctx)
+        except Exception:
+            pass
+
+    def close(self):
+        if self.ctx is not None:
+            for p in list(self._pinned.values()):
+                self.lib.rtx_host_free(self.ctx, p)
+            self._pinned.clear()
+            self._fin.detach()
+            self.lib.rtx_free(self.ctx)
+            self.ctx = None
+
+    # ---- memory -------------------------------------------------------
+    def empty(self, shape, dtype=np.float64):
+        return DeviceArray(self, shape, dtype)
+
+    def to_device(self, a, dtype=None):
+        a = np.ascontiguousarray(a, dtype)
+        return DeviceArray(self, a.shape, a.dtype).upload(a)
+
+    def pinned_empty(self, shape, dtype=np.float64):
+        """numpy array backed by page-locked host memory (full-rate PCIe)"""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape, dtype=np.int64))*dtype.itemsize
+        p = C.c_void_p()
+        check(self.lib.rtx_host_alloc(self.ctx, max(n, 16), C.byref(p)))
+        buf = (C.c_char*max(n, 16)).from_address(p.value)
+        a = np.frombuffer(buf, dtype=dtype, count=n//dtype.itemsize).reshape(shape)
+        self._pinned[a.ctypes.data] = p.value
+        return a
+
+    def pinned_free(self, a):
+        p = self._pinned.pop(a.ctypes.data, None)
+        if p is not None:
+            check(self.lib.rtx_host_free(self.ctx, p))
+
+    def free_bytes(self):
+        fr = C.c_size_t()
+        check(self.lib.rtx_device_info(self.ctx, None, C.byref(fr), None, None, 0))
+        return fr.value
+
+    def sync(self):
+        check(self.lib.rtx_sync(self.ctx))
+
+    # ---- timing -------------------------------------------------------
+    def timer_start(self):
+        check(self.lib.rtx_timer_start(self.ctx))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(self.lib.rtx_timer_stop(self.ctx, C.byref(ms)))
+        return ms.value
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        check(self.lib.rtx_last_kernel_ms(self.ctx, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self.lib.rtx_launch_count(self.ctx))
+
+    # ---- the hot path -------------------------------------------------
+    @staticmethod
+    def _table(table):
+        table = np.ascontiguousarray(table, SURFACE_DTYPE)
+        if table.ndim != 1 or len(table) < 1:
+            raise ValueError("surface table must be a non-empty 1-d record array")
+        return table
+
+    @staticmethod
+    def _flags(exact, direct):
+        return (RTX_EXACT if exact else 0) | (RTX_STORE_DIRECT if direct else 0)
+
+    def trace_device(self, table, y0, u0, Y, U, I, T, N=None, ld=None, clip=False,
+                     keep_last=False, rot0=None, exact=False, direct=False):
+        """One launch on DEVICE arrays (DeviceArray or None for outputs).
+        Asynchronous on the engine stream."""
+        table = self._table(table)
+        dt = _code(y0.dtype)
+        N = y0.shape[0] if N is None else int(N)
+        first = next(a for a in (Y, U, I, T) if a is not None)
+        ld = first.shape[1] if ld is None else int(ld)
+        r0 = None if rot0 is None else np.ascontiguousarray(rot0, np.float64).reshape(9)
+        dp = lambda a: None if a is None else a.ptr  # noqa: E731
+        check(self.lib.rtx_trace(
+            self.ctx, ptr(table), len(table), ptr(r0), dt, N, y0.ptr, u0.ptr,
+            int(bool(clip)), RTX_KEEP_LAST if keep_last else RTX_KEEP_ALL, ld,
+            dp(Y), dp(U), dp(I), dp(T), self._flags(exact, direct)))
+
+    def trace(self, table, y0, u0, clip=False, keep_last=False, rot0=None,
+              dtype=np.float64, exact=False, direct=False, out=None,
+              want=("y", "u", "i", "t")):
+        """Host arrays in, host arrays out (reference layout): returns
+        Y,U,I (rows,N,3), T (rows,N); rows = S or 1.  H2D, kernel and D2H are
+        pipelined over ray chunks inside the library."""
+        table = self._table(table)
+        dtype = np.dtype(dtype)
+        dt = _code(dtype)
+        y0 = np.ascontiguousarray(y0, dtype)
+        u0 = np.ascontiguousarray(u0, dtype)
+        if y0.ndim != 2 or y0.shape[1] != 3 or u0.shape != y0.shape:
+            raise ValueError("y0, u0 must both be (N, 3)")
+        N = y0.shape[0]
+        rows = 1 if keep_last else len(table)
+        if out is None:
+            out = {}
+        res = []
+        for k, shape in (("y", (rows, N, 3)), ("u", (rows, N, 3)),
+                         ("i", (rows, N, 3)), ("t", (rows, N))):
+            if k not in want:
+                res.append(None)
+                continue
+            a = out.get(k)
+            if a is None:
+                a = np.empty(shape, dtype)
+            if a.shape != shape or a.dtype != dtype or not a.flags.c_contiguous:
+                raise ValueError("output %r must be C-contiguous %s %r" % (k, dtype, shape))
+            res.append(a)
+        r0 = None if rot0 is None else np.ascontiguousarray(rot0, np.float64).reshape(9)
+        check(self.lib.rtx_trace_host(
+            self.ctx, ptr(table), len(table), ptr(r0), dt, N, ptr(y0), ptr(u0),
+            int(bool(clip)), RTX_KEEP_LAST if keep_last else RTX_KEEP_ALL,
+            ptr(res[0]), ptr(res[1]), ptr(res[2]), ptr(res[3]),
+            self._flags(exact, direct)))
+        return tuple(res)
+
+    def moments(self, y, w=None, N=None):
+        """Weighted moments of device intercepts (include/rtx.h rtx_moments)."""
+        m = np.zeros(6)
+        N = y.shape[-2] if N is None else int(N)
+        check(self.lib.rtx_moments(self.ctx, _code(y.dtype), N, y.ptr,
+                                   None if w is None else w.ptr, ptr(m)))
+        return m
+
+
+_default = {}
+
+
+def default_engine(device=0):
+    """process-wide engine for `device` (created on first use)"""
+    e = _default.get(device)
+    if e is None or e.ctx is None:
+        e = _default[device] = Engine(device)
+    return e

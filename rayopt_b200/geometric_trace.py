@@ -1,0 +1,208 @@
+"""GPU drop-in for rayopt's real-ray trace driver.
+
+Mirrors ``rayopt.geometric_trace.GeometricTrace`` (rayopt/geometric_trace.py)
+for the hot path: same constructor, same ``allocate / rays_given / propagate``
+signatures, same result attributes ``y, u, i (S+1, N, 3)``, ``t (S+1, N)``,
+``n (S+1,)``, ``w, ref, l, nrays`` as numpy arrays -- but ``propagate`` is ONE
+CUDA launch through the C ABI (include/rtx.h) instead of the Python loop over
+``System.propagate`` (rayopt/system.py:459-464).  There is no CPU fallback.
+
+Two ways to use it:
+
+* standalone ``GeometricTrace(system)``: `system` is a rayopt ``System`` or any
+  sequence of elements exposing what ``surface_table.pack_system`` reads;
+* ``bind(rayopt.GeometricTrace)`` returns a subclass of the reference class
+  whose ``allocate``/``propagate`` are replaced, so that ``rays_point``,
+  ``rays_clipping``, ``refocus``, ``opd``, ``Analysis`` ... keep working
+  unchanged.
+"""
+import weakref
+
+import numpy as np
+
+from .engine import default_engine
+from .surface_table import pack_system
+
+# result arrays above this size are allocated page-locked so that the D2H of a
+# full trace runs at PCIe rate
+PINNED_THRESHOLD = 8 << 20
+
+
+class PropagateMixin:
+    """`allocate` and `propagate` of GeometricTrace on the GPU engine."""
+
+    engine = None        # rayopt_b200.engine.Engine; default: process-wide
+    dtype = np.float64   # float32 selects the FP32 kernels (results cast up)
+    exact = False        # RTX_EXACT: bit-identical-to-numpy FP64 arithmetic
+    clip_default = False
+
+    def _engine(self):
+        if self.engine is None:
+            self.engine = default_engine()
+        return self.engine
+
+    def _empty(self, shape):
+        n = int(np.prod(shape))*8
+        if n >= PINNED_THRESHOLD:
+            eng = self._engine()
+            a = eng.pinned_empty(shape, np.float64)
+            weakref.finalize(self, _release, weakref.ref(eng), a.ctypes.data)
+            return a
+        return np.empty(shape)
+
+    def allocate(self, nrays):
+        """rayopt/geometric_trace.py:37-47"""
+        self.length = len(self.system)          # Trace.allocate, raytrace.py:29
+        self.nrays = nrays
+        self.n = np.empty(self.length)
+        self.y = self._empty((self.length, nrays, 3))
+        self.u = self._empty((self.length, nrays, 3))
+        self.i = self._empty((self.length, nrays, 3))
+        self.w = None
+        self.ref = None
+        self.l = 1.
+        self.t = self._empty((self.length, nrays))
+
+    def _cache_system(self):
+        """Trace.propagate, rayopt/raytrace.py:32-36"""
+        for name in ("path", "track", "origins", "mirrored"):
+            try:
+                setattr(self, name, getattr(self.system, name))
+            except AttributeError:
+                pass
+
+    def propagate(self, start=1, stop=None, clip=False):
+        """rayopt/geometric_trace.py:72-80 -- one launch instead of S numpy
+        passes.  Rows start..stop-1 of y,u,i,t,n are overwritten."""
+        self._cache_system()
+        init = start - 1
+        table, n, rot0 = pack_system(self.system, self.l, start, stop,
+                                     n0=self.n[init])
+        rows = len(table)
+        if rows == 0:
+            return
+        sl = slice(start, start + rows)
+        eng = self._engine()
+        if np.dtype(self.dtype) == np.float64:
+            eng.trace(table, self.y[init], self.u[init], clip=clip, rot0=rot0,
+                      exact=self.exact,
+                      out={"y": self.y[sl], "u": self.u[sl], "i": self.i[sl],
+                           "t": self.t[sl]})
+        else:
+            Y, U, I, T = eng.trace(table, self.y[init], self.u[init], clip=clip,
+                                   rot0=rot0, dtype=self.dtype)
+            self.y[sl], self.u[sl], self.i[sl], self.t[sl] = Y, U, I, T
+        self.n[sl] = n
+
+
+def _release(engine_ref, address):
+    eng = engine_ref()
+    if eng is not None and eng.ctx is not None:
+        p = eng._pinned.pop(address, None)
+        if p is not None:
+            eng.lib.rtx_host_free(eng.ctx, p)
+
+
+class GeometricTrace(PropagateMixin):
+    """Standalone drop-in (no rayopt import needed)."""
+
+    def __init__(self, system, engine=None, dtype=np.float64, exact=False):
+        self.system = system
+        self.engine = engine
+        self.dtype = dtype
+        self.exact = exact
+
+    def rays_given(self, y, u, l=None, w=None, ref=0):
+        """rayopt/geometric_trace.py:49-70"""
+        y, u = np.atleast_2d(y, u)
+        y, u = np.broadcast_arrays(y, u)
+        n, m = y.shape
+        if not hasattr(self, "y") or self.y.shape[1] != n:
+            self.allocate(n)
+        if l is None:
+            l = self.system.wavelengths[0]
+        if w is None:
+            w = np.ones(n)/n
+        self.w = w
+        self.ref = ref
+        self.l = l
+        self.y[0, :, :m] = y
+        self.y[0, :, m:] = 0
+        self.u[0, :, :m] = u
+        if m < 3:  # assumes forward rays
+            u2 = np.square(self.u[0, :, :2]).sum(-1)
+            self.u[0, :, 2] = np.sqrt(1 - u2)
+        self.i[0] = self.u[0]
+        self.n[0] = self.system.refractive_index(l, 0)
+        self.t[0] = 0
+
+    def rms(self, i=-1, ref=None):
+        """rayopt/geometric_trace.py:171-183 (not NaN-masked, like the reference)"""
+        y = self.y[i, :, :2]
+        y0 = y.mean(0) if ref is None else y[ref]
+        r = np.square(y - y0).sum(1)
+        w = self.w if self.w is not None else np.ones_like(r)/r.shape[0]
+        return np.sqrt((r*w).sum())
+
+    def refocus(self, at=-1):
+        """rayopt/geometric_trace.py:82-99"""
+        y = self.y[at, :, :2]
+        i = self.i[at]
+        u = i[:, :2]/i[:, 2:]                   # tanarcsin, utils.py:42-48
+        good = np.all(np.isfinite(u), axis=1)
+        y, u = y[good], u[good]
+        w = self.w[good] if self.w is not None else np.ones(y.shape[0])
+        y = y - y.mean(0)
+        u = u - u.mean(0)
+        wy = (w[:, None]*y).ravel()
+        wu = (w[:, None]*u).ravel()
+        u = u.ravel()
+        t = -np.dot(wy, u)/np.dot(wu, u)
+        self.system[at].distance += t
+        self.propagate()
+
+
+def bind(reference_trace_class, engine=None, dtype=np.float64, exact=False):
+    """Subclass of the reference's GeometricTrace with the hot path replaced.
+
+        import rayopt, rayopt_b200
+        GT = rayopt_b200.bind(rayopt.GeometricTrace)
+        t = GT(system); t.rays_point((0, 1.), nrays=10**6, distribution="hexapolar")
+    """
+    return type("GeometricTrace", (PropagateMixin, reference_trace_class),
+                {"engine": engine, "dtype": dtype, "exact": exact,
+                 "__doc__": reference_trace_class.__doc__})
+
+
+def system_propagate(system, y, u, n, l, start=1, stop=None, clip=False,
+                     engine=None, exact=False):
+    """System.propagate (rayopt/system.py:459-464) as one launch: a generator
+    yielding ``(y, u, n, i, t)`` per surface in the surface-normal frame.
+    Input rays are in the lab frame of ``system[start-1]`` (i.e. AFTER its
+    from_normal), as for the reference generator."""
+    eng = engine or default_engine()
+    table, ns, _ = pack_system(system, l, start, stop, n0=n)
+    if len(table) == 0:
+        return
+    y, u = np.atleast_2d(y, u)
+    Y, U, I, T = eng.trace(table, y, u, clip=clip, exact=exact)
+    for j in range(len(table)):
+        yield Y[j], U[j], ns[j], I[j], T[j]
+
+
+def install(system_class, trace_class=None, engine=None, exact=False):
+    """Monkey-patch a rayopt ``System`` class (and optionally its
+    ``GeometricTrace``) so that every caller -- aim_chief / aim_marginal
+    (rayopt/system.py:507-555), Analysis -- runs on the GPU engine."""
+    def propagate(self, y, u, n, l, start=1, stop=None, clip=False):
+        return system_propagate(self, y, u, n, l, start, stop, clip,
+                                engine=engine, exact=exact)
+    system_class.propagate = propagate
+    if trace_class is not None:
+        trace_class.allocate = PropagateMixin.allocate
+        trace_class.propagate = PropagateMixin.propagate
+        for k in ("_engine", "_empty", "_cache_system"):
+            setattr(trace_class, k, getattr(PropagateMixin, k))
+        trace_class.engine = engine
+        trace_class.dtype = np.float64
+        trace_class.exact = exact

@@ -1,0 +1,45 @@
+"""Launch-ray generation for aimed bundles (host numpy).
+
+Restates, for the cases the benchmark workloads need, what the reference does
+upstream of the hot path:  ``InfiniteConjugate.aim`` with the rectilinear
+projection (rayopt/conjugates.py:208-213, 236-255), ``Pupil.map`` with
+``filter=False`` (rayopt/pupils.py:97-107) and ``sagittal_meridional``
+(rayopt/utils.py:102-114), given a pupil-aiming solution ``(z, p)`` that the
+reference's ``System.pupil`` solved on the host (rayopt/system.py:585-593).
+The object surface (``system[0]``) is taken to be a plane, as in every fixture.
+"""
+import numpy as np
+
+
+def disc(n, seed):
+    """uniform pupil coordinates in the unit disc: r = sqrt(U), phi = 2 pi U"""
+    rng = np.random.default_rng(seed)
+    r = np.sqrt(rng.random(n))
+    phi = 2*np.pi*rng.random(n)
+    return np.c_[r*np.cos(phi), r*np.sin(phi)]
+
+
+def aim_infinite(yo, yp, z, p, angle):
+    """Rays (y, u), each (N, 3), for fractional object coordinate `yo` (2,),
+    fractional pupil coordinates `yp` (N, 2), pupil distance `z`, pupil
+    half-apertures `p` (2, 2) and object semi-angle `angle` (radians)."""
+    yo = np.atleast_2d(np.asarray(yo, float))
+    yp = np.atleast_2d(np.asarray(yp, float))
+    p = np.asarray(p, float)
+    yp = yp*np.fabs(p).max()                               # pupils.py:100-101
+    yo, yp = np.broadcast_arrays(yo, yp)
+    n = yo.shape[0]
+    yt = yo*np.tan(angle)                                  # conjugates.py:211
+    u = np.hstack((yt, np.ones((n, 1))))
+    u /= np.sqrt(np.square(u).sum(-1))[:, None]
+    yz = np.array((0, 0, z), float)
+    y = yz - z*u                                           # conjugates.py:249
+    s = np.cross(u, yz)                                    # utils.py:103-110
+    axial = np.all(s == 0, axis=-1)[..., None]
+    s = np.where(axial, (1., 0, 0), s)
+    m = np.cross(u, s)
+    s /= np.sqrt(np.square(s).sum(-1))[..., None]
+    m /= np.sqrt(np.square(m).sum(-1))[..., None]
+    y += yp[..., 0, None]*s + yp[..., 1, None]*m           # conjugates.py:252
+    y += (-y[:, 2]/u[:, 2])[..., None]*u                   # plane object surface, :254
+    return y, u

@@ -1,0 +1,212 @@
+"""Parity of the CUDA engine (through the C ABI) with the oracle and the
+golden vectors of the live reference.  Needs a GPU: `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+import np_oracle
+from conftest import golden_names, load_golden, load_systems, assert_parity
+from rayopt_b200.rays import aim_infinite, disc
+
+pytestmark = pytest.mark.gpu
+
+FP64_RTOL = 1e-10     # north_star: <= 1e-10 rel for FP64
+FP32_RTOL = 1e-5      # north_star: <= 1e-5 rel for FP32
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from rayopt_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _cmp(got, c, rtol, tag):
+    worst = 0.
+    for a, b, w in zip(got, (c["Y"], c["U"], c["I"], c["T"]), "yuit"):
+        worst = max(worst, assert_parity(a, b, rtol, "%s %s %s" % (c["name"], tag, w)))
+    return worst
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_exact_mode_vs_reference_golden(eng, name):
+    """RTX_EXACT: bit-identical to the reference on unrotated analytic
+    systems; a few ulp where the reference itself goes through BLAS dot
+    products (rotations, Newton fprime)."""
+    c = load_golden(name)
+    got = eng.trace(c["table"], c["y0"], c["u0"], clip=c["clip"], rot0=c["rot0"], exact=True)
+    newton = bool((c["table"]["n_asph"] >= 0).any())
+    if not c["rotated"] and not newton:
+        for a, b, w in zip(got, (c["Y"], c["U"], c["I"], c["T"]), "yuit"):
+            assert np.array_equal(a, b, equal_nan=True), "%s %s not bit-exact" % (name, w)
+    else:
+        _cmp(got, c, 1e-12, "exact")
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fast_mode_vs_reference_golden(eng, name):
+    c = load_golden(name)
+    got = eng.trace(c["table"], c["y0"], c["u0"], clip=c["clip"], rot0=c["rot0"])
+    _cmp(got, c, FP64_RTOL, "fast")
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fp32_vs_reference_golden(eng, name):
+    c = load_golden(name)
+    if name.startswith(("newton_edge", "conics", "parabola")):
+        pytest.skip("ill-conditioned edge cases: NaN mask is precision dependent")
+    got = eng.trace(c["table"], c["y0"], c["u0"], clip=c["clip"], rot0=c["rot0"],
+                    dtype=np.float32)
+    # rays within FP32 resolution of an aperture edge / TIR may flip: compare
+    # where both are finite, and bound the number of mask flips
+    flips = 0
+    for a, b, w in zip(got, (c["Y"], c["U"], c["I"], c["T"]), "yuit"):
+        a = a.astype(np.float64)
+        m = np.isnan(a) != np.isnan(b)
+        flips = max(flips, int(m.sum()))
+        a = np.where(m, b, a)
+        assert_parity(a, b, FP32_RTOL, "%s fp32 %s" % (name, w))
+    assert flips <= max(2, c["y0"].shape[0]//100)*3*len(c["table"]), flips
+
+
+@pytest.mark.parametrize("name", ["double_gauss_l0_clip", "cooke_asph_f07_clip",
+                                  "tilted_clip1", "singlet_c1"])
+def test_store_paths_identical(eng, name):
+    """TMA bulk-store path == per-thread store path, bit for bit"""
+    c = load_golden(name)
+    for exact in (False, True):
+        a = eng.trace(c["table"], c["y0"], c["u0"], clip=c["clip"], rot0=c["rot0"], exact=exact)
+        b = eng.trace(c["table"], c["y0"], c["u0"], clip=c["clip"], rot0=c["rot0"], exact=exact,
+                      direct=True)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y, equal_nan=True)
+
+
+def test_keep_last_and_null_outputs(eng):
+    c = load_golden("zoom_f1_clip")
+    full = eng.trace(c["table"], c["y0"], c["u0"], clip=True)
+    last = eng.trace(c["table"], c["y0"], c["u0"], clip=True, keep_last=True)
+    for a, b in zip(full, last):
+        assert b.shape[0] == 1
+        assert np.array_equal(a[-1], b[0], equal_nan=True)
+    y, u, i, t = eng.trace(c["table"], c["y0"], c["u0"], clip=True, want=("y",))
+    assert u is None and i is None and t is None
+    assert np.array_equal(y, full[0], equal_nan=True)
+
+
+def test_device_arrays_any_pitch(eng):
+    """rtx_trace on device buffers: ld = N (odd, direct stores) and ld
+    padded to 64 (bulk stores) give the same rows"""
+    c = load_golden("double_gauss_f1_noclip")
+    N, S = c["y0"].shape[0] - 3, len(c["table"])     # odd N
+    y0 = eng.to_device(c["y0"][:N])
+    u0 = eng.to_device(c["u0"][:N])
+    for ld in (N, 320):
+        Y, U, I = (eng.empty((S, ld, 3)) for _ in range(3))
+        T = eng.empty((S, ld))
+        eng.trace_device(c["table"], y0, u0, Y, U, I, T, N=N, ld=ld, clip=False)
+        eng.sync()
+        assert_parity(Y.download()[:, :N], c["Y"][:, :N], FP64_RTOL, "Y ld=%d" % ld)
+        assert_parity(U.download()[:, :N], c["U"][:, :N], FP64_RTOL, "U ld=%d" % ld)
+        assert_parity(I.download()[:, :N], c["I"][:, :N], FP64_RTOL, "I ld=%d" % ld)
+        assert_parity(T.download()[:, :N], c["T"][:, :N], FP64_RTOL, "T ld=%d" % ld)
+        for a in (Y, U, I, T):
+            a.free()
+
+
+@pytest.mark.parametrize("sysname,n,clip", [("double_gauss", 300000, True),
+                                            ("zoom", 200000, True),
+                                            ("cooke_asph", 100000, True),
+                                            ("cooke", 100000, False)])
+def test_large_bundle_vs_oracle(eng, systems, sysname, n, clip):
+    """sizes the oracle finishes in seconds: multi-chunk grid, ragged tail"""
+    ent = systems[sysname]
+    n += 37                                       # ragged: not a multiple of 32
+    for li in range(min(2, len(ent["tables"]))):
+        table = ent["tables"][li]
+        aim = ent["aim"][li][3]                   # field (0, .7)
+        y0, u0 = aim_infinite(aim["field"], disc(n, 5 + li), aim["z"], aim["p"],
+                              ent["object_angle"])
+        want = np_oracle.trace(table, y0, u0, clip=clip)
+        newton = bool((table["n_asph"] >= 0).any())
+        got = eng.trace(table, y0, u0, clip=clip, exact=True)
+        for a, b, w in zip(got, want, "yuit"):
+            if newton:
+                assert_parity(a, b, 1e-12, "%s exact %s" % (sysname, w))
+            else:
+                assert np.array_equal(a, b, equal_nan=True), (sysname, w)
+        got = eng.trace(table, y0, u0, clip=clip)
+        for a, b, w in zip(got, want, "yuit"):
+            assert_parity(a, b, FP64_RTOL, "%s fast %s" % (sysname, w))
+
+
+def test_known_answer_rms_through_dropin(eng):
+    """rayopt/test/test_raytrace.py:192-195 through the CUDA path"""
+    c = load_golden("cooke_radau13")
+    Y, U, I, T = eng.trace(c["table"], c["y0"], c["u0"], exact=True)
+    rms = np_oracle.rms(Y[-1], c["w"])
+    assert abs(rms - 0.052)/0.052 < 1e-2
+    assert rms == c["meta"]["rms"]
+
+
+def test_moments_match_rms(eng):
+    c = load_golden("double_gauss_l1_clip")
+    N = c["y0"].shape[0]
+    Y = eng.to_device(c["Y"][-1])
+    w = eng.to_device(np.full(N, 1.0/N))
+    m = eng.moments(Y, w)
+    y = c["Y"][-1, :, :2]
+    good = np.isfinite(y).all(1)
+    assert m[4] == good.sum() and m[5] == N
+    np.testing.assert_allclose(m[0], good.sum()/N, rtol=1e-13)
+    np.testing.assert_allclose(m[1:3], (y[good]/N).sum(0), rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(m[3], (np.square(y[good]).sum(1)/N).sum(), rtol=1e-12)
+
+
+def test_empty_and_bad_arguments(eng):
+    c = load_golden("singlet_c1")
+    out = eng.trace(c["table"], np.zeros((0, 3)), np.zeros((0, 3)))
+    assert out[0].shape == (3, 0, 3)
+    from rayopt_b200._lib import RtxError
+    bad = c["table"].copy()
+    bad["n_asph"][0] = 99
+    with pytest.raises(RtxError):
+        eng.trace(bad, c["y0"], c["u0"])
+    with pytest.raises(RtxError):
+        eng.trace(c["table"], c["y0"], c["u0"], dtype=np.float32, exact=True)
+
+
+def test_round_trip_properties_full_size(eng, systems):
+    """size-independent properties at a BASELINE-scale bundle (1e7 rays, 12
+    surfaces, FP64): directions stay unit length, intercepts lie on their
+    surfaces (sag residual), optical path is additive, NaN is absorbing."""
+    ent = systems["double_gauss"]
+    table = ent["tables"][0]
+    aim = ent["aim"][0][3]
+    n = 10_000_000
+    y0, u0 = aim_infinite(aim["field"], disc(n, 0), aim["z"], aim["p"], ent["object_angle"])
+    S = len(table)
+    d_y0, d_u0 = eng.to_device(y0), eng.to_device(u0)
+    ld = ((n + 63)//64)*64
+    Y, U = eng.empty((S, ld, 3)), eng.empty((S, ld, 3))
+    eng.trace_device(table, d_y0, d_u0, Y, U, None, None, N=n, ld=ld, clip=True)
+    eng.sync()
+    rng = np.random.default_rng(0)
+    for j in (0, 4, 5, S - 1):
+        y = Y.rows(j).download()[0, :n]
+        u = U.rows(j).download()[0, :n]
+        ok = np.isfinite(u[:, 0])
+        # unit directions (refract keeps |u| = 1 to ~2e-16)
+        assert np.abs(np.square(u[ok]).sum(1) - 1).max() < 1e-13
+        # intercepts on the surface
+        res = np_oracle.surface_sag(table[j], y[np.isfinite(y[:, 0])][::97])
+        assert np.abs(res).max() < 1e-11
+        if j == S - 1:
+            assert 0.90 < ok.mean() < 0.97        # ~6 % vignetted
+    # a sample against the oracle
+    idx = rng.choice(n, 5000, replace=False)
+    want = np_oracle.trace(table, y0[idx], u0[idx], clip=True)
+    got_y = np.stack([Y.rows(j).download()[0][idx] for j in range(S)])
+    assert_parity(got_y, want[0], FP64_RTOL, "1e7 sample y")
+    for a in (Y, U, d_y0, d_u0):
+        a.free()
