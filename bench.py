@@ -73,7 +73,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -160,12 +160,13 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--exact", type=int, default=0, help="1: RTX_EXACT arithmetic")
     ap.add_argument("--direct", type=int, default=0, help="1: per-thread stores")
+    ap.add_argument("--rpt", type=int, default=0, help="rays per thread (0: library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -205,7 +206,7 @@ def main():
             d = dev[li]
             eng.trace_device(ent["tables"][li], d["y0"], d["u0"], d["Y"], d["U"], d["I"],
                              d["T"], N=N, ld=ld, clip=True, exact=bool(args.exact),
-                             direct=bool(args.direct))
+                             direct=bool(args.direct), rpt=args.rpt)
 
     def barrier():
         eng.sync()
@@ -243,7 +244,7 @@ def main():
             d = dev[li]
             eng.trace_device(ent["tables"][li], d["y0"], d["u0"], d["Y"], d["U"], d["I"],
                              d["T"], N=N, ld=ld, clip=True, exact=bool(args.exact),
-                             direct=bool(args.direct))
+                             direct=bool(args.direct), rpt=args.rpt)
             per_launch.append(eng.last_kernel_ms())
     k_ms = statistics.mean(per_launch)
     alg_bytes = N*(6*w + 10*w*S)
@@ -278,7 +279,7 @@ def main():
         def e2e_step():
             for li in range(nl):
                 eng.trace(ent["tables"][li], pin[li][0], pin[li][1], clip=True, out=out,
-                          exact=bool(args.exact))
+                          exact=bool(args.exact), rpt=args.rpt)
         e2e_steps = max(1, min(args.steps, 3))
         e2e_step()
         barrier()
@@ -317,6 +318,7 @@ def main():
                        "wavelengths": nl, "parallelism": "rays sharded x%d" % world,
                        "arithmetic": "exact" if args.exact else "fast",
                        "stores": "direct" if args.direct else "tma-bulk",
+                       "rays_per_thread": args.rpt or int(os.environ.get("RTX_RPT", "1")),
                        "l2": "outputs %.1f GB per launch >> 126 MB L2 (no flush needed)"
                              % (alg_bytes/1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

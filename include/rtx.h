@@ -69,6 +69,8 @@ extern "C" {
                              on unrotated analytic surfaces) */
 #define RTX_STORE_DIRECT 2u /* debug: force per-thread strided stores instead
                                of the shared-memory staged bulk (TMA) stores */
+#define RTX_RPT1       4u /* tuning: one ray per thread  (default: library's choice) */
+#define RTX_RPT2       8u /* tuning: two rays per thread */
 
 /* errors */
 #define RTX_OK              0
@@ -195,15 +197,31 @@ int rtx_trace_host(rtx_ctx *ctx, const rtx_surface *surf, int S,
                    const void *y0, const void *u0, int clip, int keep,
                    void *Y, void *U, void *I, void *T, unsigned flags);
 
+/* ---- self-test --------------------------------------------------------- */
+/*
+ * The kernels use their own branch-free FP64 division / sqrt / rsqrt (the
+ * library sequences minus the slow-path subroutine).  For n host operand
+ * pairs (a, b) writes 6*n doubles to `out` (host): a/b (engine), a/b (IEEE
+ * __ddiv_rn), sqrt(a) (engine), sqrt(a) (IEEE), 1/sqrt(a) (engine),
+ * 1/sqrt(a) (IEEE).
+ */
+int rtx_selftest_math(rtx_ctx *ctx, int64_t n, const double *a, const double *b,
+                      double *out);
+
 /* ---- fused last-surface reductions (geometric_trace.py:171-183) ------- */
 /*
- * Weighted moments of DEVICE intercepts y (N,3), dtype as given:
- * m[0]=sum w, m[1]=sum w*x, m[2]=sum w*y, m[3]=sum w*(x^2+y^2),
- * m[4]=count finite, m[5]=count total.  Rays with non-finite x or y are
- * skipped (counted in m[5] only).  w may be NULL (w = 1).  m: host, 6 doubles.
+ * Weighted moments of DEVICE intercepts y (N,3), dtype as given, about
+ * `center` (host, 2 doubles, or NULL for the origin); dx = x - center[0]:
+ * m[0]=sum w, m[1]=sum w*dx, m[2]=sum w*dy, m[3]=sum w*(dx^2+dy^2),
+ * m[4]=count finite, m[5]=count total, m[6]=sum dx, m[7]=sum dy.
+ * Rays with non-finite x or y are skipped (counted in m[5] only).
+ * w (device, N values of dtype) may be NULL (w = 1).  m: host, 8 doubles.
+ * Two calls (moments about 0, then about the mean) give the reference's
+ * rms() without moving y to the host; per-rank moments add up
+ * (all-reduce of 8 doubles) for ray-sharded multi-GPU runs.
  */
 int rtx_moments(rtx_ctx *ctx, int dtype, int64_t N, const void *y,
-                const void *w, double *m);
+                const void *w, const double *center, double *m);
 
 #ifdef __cplusplus
 }

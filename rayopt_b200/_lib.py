@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "librtx.so")
 
 RTX_F64, RTX_F32 = 0, 1
 RTX_KEEP_ALL, RTX_KEEP_LAST = 0, 1
-RTX_EXACT, RTX_STORE_DIRECT = 1, 2
+RTX_EXACT, RTX_STORE_DIRECT, RTX_RPT1, RTX_RPT2 = 1, 2, 4, 8
 
 # every symbol include/rtx.h declares: name -> (restype, argtypes)
 _vp, _i, _i64, _sz, _u = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_uint
@@ -45,7 +45,8 @@ SYMBOLS = {
                        _vp, _vp, _vp, _vp, _u]),
     "rtx_trace_host": (_i, [_vp, _vp, _i, _vp, _i, _i64, _vp, _vp, _i, _i,
                             _vp, _vp, _vp, _vp, _u]),
-    "rtx_moments": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
+    "rtx_moments": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp]),
+    "rtx_selftest_math": (_i, [_vp, _i64, _vp, _vp, _vp]),
 }
 
 _lib = None

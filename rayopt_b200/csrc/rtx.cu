@@ -59,6 +59,7 @@ struct rtx_ctx {
     double* d_moments = nullptr;
     int64_t launches = 0;
     int max_smem_optin = 0;
+    int default_rpt = 1;
 };
 
 namespace {
@@ -125,18 +126,19 @@ int ensure_slots(rtx_ctx* ctx, size_t bytes) {
     return 0;
 }
 
-template <typename T, bool EXACT, bool BULK>
+template <typename T, bool EXACT, int RPT, bool BULK>
 int launch_one(rtx_ctx* ctx, const TraceParams<T>& p, cudaStream_t stream) {
-    auto kern = trace_kernel<T, EXACT, BULK>;
-    size_t smem = trace_smem_bytes<T>(p.S, BULK);
+    auto kern = trace_kernel<T, EXACT, RPT, BULK>;
+    size_t smem = trace_smem_bytes<T, RPT>(p.S, BULK);
     if ((int)smem > ctx->max_smem_optin) return RTX_E_UNSUPPORTED;
     if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
     if (occ < 1) occ = 1;
-    long long tiles = (p.N + THREADS - 1) / THREADS;
-    long long grid = (long long)ctx->sm_count * occ;
+    const long long per_cta = (long long)THREADS * RPT;
+    long long tiles = (p.N + per_cta - 1) / per_cta;
+    long long grid = (long long)ctx->sm_count * occ;  // persistent: one wave
     if (grid > tiles) grid = tiles;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, THREADS, smem, stream>>>(p);
@@ -144,25 +146,28 @@ int launch_one(rtx_ctx* ctx, const TraceParams<T>& p, cudaStream_t stream) {
     return (int)cudaGetLastError();
 }
 
+template <typename T, bool EXACT>
+int launch_rpt(rtx_ctx* ctx, const TraceParams<T>& p, int rpt, bool bulk, cudaStream_t stream) {
+    if (!bulk) return launch_one<T, EXACT, 1, false>(ctx, p, stream);
+    if (rpt == 2) return launch_one<T, EXACT, 2, true>(ctx, p, stream);
+    return launch_one<T, EXACT, 1, true>(ctx, p, stream);
+}
+
 template <typename T>
-int launch_trace(rtx_ctx* ctx, const TraceParams<T>& p, bool exact, bool bulk,
+int launch_trace(rtx_ctx* ctx, const TraceParams<T>& p, bool exact, int rpt, bool bulk,
                  cudaStream_t stream);
 
 template <>
-int launch_trace<double>(rtx_ctx* ctx, const TraceParams<double>& p, bool exact, bool bulk,
-                         cudaStream_t stream) {
-    if (exact)
-        return bulk ? launch_one<double, true, true>(ctx, p, stream)
-                    : launch_one<double, true, false>(ctx, p, stream);
-    return bulk ? launch_one<double, false, true>(ctx, p, stream)
-                : launch_one<double, false, false>(ctx, p, stream);
+int launch_trace<double>(rtx_ctx* ctx, const TraceParams<double>& p, bool exact, int rpt,
+                         bool bulk, cudaStream_t stream) {
+    if (exact) return launch_rpt<double, true>(ctx, p, rpt, bulk, stream);
+    return launch_rpt<double, false>(ctx, p, rpt, bulk, stream);
 }
 template <>
-int launch_trace<float>(rtx_ctx* ctx, const TraceParams<float>& p, bool exact, bool bulk,
+int launch_trace<float>(rtx_ctx* ctx, const TraceParams<float>& p, bool exact, int rpt, bool bulk,
                         cudaStream_t stream) {
     if (exact) return RTX_E_UNSUPPORTED;  // RTX_EXACT is FP64 only
-    return bulk ? launch_one<float, false, true>(ctx, p, stream)
-                : launch_one<float, false, false>(ctx, p, stream);
+    return launch_rpt<float, false>(ctx, p, rpt, bulk, stream);
 }
 
 // convert + upload the table; returns the device pointer.  The copy is
@@ -221,9 +226,13 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
     p.I = (T*)I;
     p.Tt = (T*)Tt;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    bool bulk = !(flags & RTX_STORE_DIRECT) && (ld % 32 == 0) && al16(Y) && al16(U) && al16(I) &&
-                al16(Tt);
-    return launch_trace<T>(ctx, p, (flags & RTX_EXACT) != 0, bulk, stream);
+    int rpt = ctx->default_rpt;
+    if (flags & RTX_RPT1) rpt = 1;
+    if (flags & RTX_RPT2) rpt = 2;
+    if (N <= 32 * 1024) rpt = 1;  // small bundles: spread over more warps
+    bool bulk = !(flags & RTX_STORE_DIRECT) && (ld % (32 * rpt) == 0) && al16(Y) && al16(U) &&
+                al16(I) && al16(Tt);
+    return launch_trace<T>(ctx, p, (flags & RTX_EXACT) != 0, rpt, bulk, stream);
 }
 
 int ensure_chunk(rtx_ctx* ctx, ChunkBuf& cb, size_t in_bytes, size_t out3, size_t out1) {
@@ -405,7 +414,11 @@ int rtx_init(int device, rtx_ctx** out) {
     CK(cudaEventCreate(&ctx->t1));
     CK(cudaEventCreate(&ctx->k0));
     CK(cudaEventCreate(&ctx->k1));
-    CK(cudaMalloc((void**)&ctx->d_moments, 6 * sizeof(double)));
+    CK(cudaMalloc((void**)&ctx->d_moments, 8 * sizeof(double)));
+    if (const char* e = getenv("RTX_RPT")) {
+        int v = atoi(e);
+        if (v == 1 || v == 2) ctx->default_rpt = v;
+    }
     *out = ctx;
     return 0;
 }
@@ -572,26 +585,48 @@ int rtx_trace_host(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* r
     return trace_host<float>(ctx, surf, S, rot0, N, y0, u0, clip, keep, Y, U, I, T, flags);
 }
 
-int rtx_moments(rtx_ctx* ctx, int dtype, int64_t N, const void* y, const void* w, double* m) {
+int rtx_selftest_math(rtx_ctx* ctx, int64_t n, const double* a, const double* b, double* out) {
+    if (!ctx || n < 1 || !a || !b || !out) return RTX_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    double *da = nullptr, *db = nullptr, *dout = nullptr;
+    CK(cudaMalloc((void**)&da, n * sizeof(double)));
+    CK(cudaMalloc((void**)&db, n * sizeof(double)));
+    CK(cudaMalloc((void**)&dout, 6 * n * sizeof(double)));
+    CK(cudaMemcpyAsync(da, a, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(db, b, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    selftest_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(da, db, dout, n);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dout);
+    return 0;
+}
+
+int rtx_moments(rtx_ctx* ctx, int dtype, int64_t N, const void* y, const void* w,
+                const double* center, double* m) {
     if (!ctx || !y || !m || N < 0) return RTX_E_BADARG;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemsetAsync(ctx->d_moments, 0, 6 * sizeof(double), ctx->stream));
+    const double cx = center ? center[0] : 0.0, cy = center ? center[1] : 0.0;
+    CK(cudaMemsetAsync(ctx->d_moments, 0, 8 * sizeof(double), ctx->stream));
     if (N > 0) {
         long long blocks = (N + 255) / 256;
         long long cap = (long long)ctx->sm_count * 8;
         if (blocks > cap) blocks = cap;
         if (dtype == RTX_F64)
             moments_kernel<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
-                (const double*)y, (const double*)w, N, ctx->d_moments);
+                (const double*)y, (const double*)w, N, cx, cy, ctx->d_moments);
         else if (dtype == RTX_F32)
             moments_kernel<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
-                (const float*)y, (const float*)w, N, ctx->d_moments);
+                (const float*)y, (const float*)w, N, cx, cy, ctx->d_moments);
         else
             return RTX_E_BADARG;
         ctx->launches++;
         CK(cudaGetLastError());
     }
-    CK(cudaMemcpyAsync(m, ctx->d_moments, 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(m, ctx->d_moments, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

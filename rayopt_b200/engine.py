@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (RTX_F32, RTX_F64, RTX_KEEP_ALL, RTX_KEEP_LAST, RTX_EXACT,
-                   RTX_STORE_DIRECT, RtxError, check, ptr)
+                   RTX_STORE_DIRECT, RTX_RPT1, RTX_RPT2, RtxError, check, ptr)
 from .surface_table import SURFACE_DTYPE
 
 _DTYPES = {np.dtype(np.float64): RTX_F64, np.dtype(np.float32): RTX_F32}
@@ -164,11 +164,12 @@ class Engine:
         return table
 
     @staticmethod
-    def _flags(exact, direct):
-        return (RTX_EXACT if exact else 0) | (RTX_STORE_DIRECT if direct else 0)
+    def _flags(exact, direct, rpt=0):
+        return ((RTX_EXACT if exact else 0) | (RTX_STORE_DIRECT if direct else 0)
+                | {0: 0, 1: RTX_RPT1, 2: RTX_RPT2}[rpt])
 
     def trace_device(self, table, y0, u0, Y, U, I, T, N=None, ld=None, clip=False,
-                     keep_last=False, rot0=None, exact=False, direct=False):
+                     keep_last=False, rot0=None, exact=False, direct=False, rpt=0):
         """One launch on DEVICE arrays (DeviceArray or None for outputs).
         Asynchronous on the engine stream."""
         table = self._table(table)
@@ -181,10 +182,10 @@ class Engine:
         check(self.lib.rtx_trace(
             self.ctx, ptr(table), len(table), ptr(r0), dt, N, y0.ptr, u0.ptr,
             int(bool(clip)), RTX_KEEP_LAST if keep_last else RTX_KEEP_ALL, ld,
-            dp(Y), dp(U), dp(I), dp(T), self._flags(exact, direct)))
+            dp(Y), dp(U), dp(I), dp(T), self._flags(exact, direct, rpt)))
 
     def trace(self, table, y0, u0, clip=False, keep_last=False, rot0=None,
-              dtype=np.float64, exact=False, direct=False, out=None,
+              dtype=np.float64, exact=False, direct=False, rpt=0, out=None,
               want=("y", "u", "i", "t")):
         """Host arrays in, host arrays out (reference layout): returns
         Y,U,I (rows,N,3), T (rows,N); rows = S or 1.  H2D, kernel and D2H are
@@ -217,16 +218,45 @@ class Engine:
             self.ctx, ptr(table), len(table), ptr(r0), dt, N, ptr(y0), ptr(u0),
             int(bool(clip)), RTX_KEEP_LAST if keep_last else RTX_KEEP_ALL,
             ptr(res[0]), ptr(res[1]), ptr(res[2]), ptr(res[3]),
-            self._flags(exact, direct)))
+            self._flags(exact, direct, rpt)))
         return tuple(res)
 
-    def moments(self, y, w=None, N=None):
-        """Weighted moments of device intercepts (include/rtx.h rtx_moments)."""
-        m = np.zeros(6)
+    def selftest_math(self, a, b):
+        """(6, n): engine a/b, IEEE a/b, engine sqrt(a), IEEE sqrt(a),
+        engine 1/sqrt(a), IEEE 1/sqrt(a)"""
+        a = np.ascontiguousarray(a, np.float64)
+        b = np.ascontiguousarray(b, np.float64)
+        out = np.empty((6, a.size))
+        check(self.lib.rtx_selftest_math(self.ctx, a.size, ptr(a), ptr(b), ptr(out)))
+        return out
+
+    def moments(self, y, w=None, N=None, center=None):
+        """Weighted moments of device intercepts about `center`
+        (include/rtx.h rtx_moments): 8 doubles."""
+        m = np.zeros(8)
         N = y.shape[-2] if N is None else int(N)
+        c = None if center is None else np.ascontiguousarray(center, np.float64)
         check(self.lib.rtx_moments(self.ctx, _code(y.dtype), N, y.ptr,
-                                   None if w is None else w.ptr, ptr(m)))
+                                   None if w is None else w.ptr, ptr(c), ptr(m)))
         return m
+
+    def rms(self, y, w=None, N=None, ref_point=None, comm_sum=None):
+        """GeometricTrace.rms (rayopt/geometric_trace.py:171-183) of device
+        intercepts `y` (N,3) without a D2H of the rays: centre = unweighted
+        mean (or `ref_point`), rms = sqrt(sum w |y - y0|^2).  Like the
+        reference it is NOT NaN-masked: any non-finite ray gives NaN.
+        `comm_sum` (callable: 8-vector -> summed 8-vector) makes it the rms of
+        a ray-sharded bundle (one all-reduce per pass)."""
+        red = comm_sum or (lambda v: v)
+        if ref_point is None:
+            m = red(self.moments(y, w, N))
+            if m[4] != m[5]:
+                return float("nan")
+            ref_point = (m[6]/m[5], m[7]/m[5])
+        m = red(self.moments(y, w, N, center=ref_point))
+        if m[4] != m[5]:
+            return float("nan")
+        return float(np.sqrt(m[3]))
 
 
 _default = {}

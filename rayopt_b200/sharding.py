@@ -1,0 +1,129 @@
+"""Ray sharding over the GPUs of one box.
+
+The path shards naturally: rays are independent, the surface table is
+replicated, there is NO exchange inside the surface loop.  One process per
+GPU; rank r owns the contiguous ray range ``bounds(N, G)[r]``.  The only
+collectives the path has are optional epilogues:
+
+* ``gather_last``  -- all-gather of last-surface intercepts ``y[-1]`` when a
+  caller needs the full spot on every rank (24 B/ray FP64);
+* ``rms``          -- all-reduce of 8 FP64 moments (rtx_moments) instead,
+  when only statistics are needed.
+
+``torch.distributed`` is plumbing only (rendezvous, NCCL/gloo collectives on
+buffers the engine owns); the engine itself is torch-free.  The tracer is
+injected so that the host logic is testable on CPU with gloo.
+"""
+import numpy as np
+
+
+def bounds(n, world):
+    """contiguous shard boundaries: rank r owns [b[r], b[r+1])"""
+    return [(r*n)//world for r in range(world + 1)]
+
+
+def shard(a, rank, world):
+    b = bounds(len(a), world)
+    return a[b[rank]:b[rank + 1]]
+
+
+class TorchComm:
+    """all-gather / all-reduce of numpy arrays over torch.distributed
+    (backend nccl on GPUs, gloo on CPU)."""
+
+    def __init__(self, dist=None, device=None):
+        if dist is None:
+            import torch.distributed as dist
+        import torch
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        if device is None:
+            device = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        self.device = device
+
+    def sum(self, v):
+        t = self.torch.as_tensor(np.asarray(v, np.float64), device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def max(self, v):
+        t = self.torch.as_tensor(np.asarray(v, np.float64), device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.cpu().numpy()
+
+    def all_gather_rows(self, local, n_total):
+        """concatenate per-rank (n_r, k) blocks (contiguous `bounds` shards)
+        into (n_total, k) on every rank; shards are padded to equal length for
+        the collective (all_gather_into_tensor needs equal sizes)."""
+        torch, dist = self.torch, self.dist
+        b = bounds(n_total, self.world)
+        per = max(b[r + 1] - b[r] for r in range(self.world))
+        k = local.shape[1]
+        send = torch.zeros((per, k), dtype=torch.float64, device=self.device)
+        send[:local.shape[0]] = torch.as_tensor(np.ascontiguousarray(local), device=self.device)
+        recv = torch.empty((self.world*per, k), dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(recv, send)
+        recv = recv.cpu().numpy().reshape(self.world, per, k)
+        return np.concatenate([recv[r, :b[r + 1] - b[r]] for r in range(self.world)])
+
+    def barrier(self):
+        self.dist.barrier()
+
+
+class LocalComm:
+    """world of one"""
+    rank, world = 0, 1
+
+    def sum(self, v):
+        return np.asarray(v, np.float64)
+
+    max = sum
+
+    def all_gather_rows(self, local, n_total):
+        return np.asarray(local)
+
+    def barrier(self):
+        pass
+
+
+class ShardedTrace:
+    """Trace a ray bundle sharded over ranks.
+
+    `tracer(table, y0, u0, clip, keep_last)` -> (Y, U, I, T) host arrays for
+    the LOCAL shard; by default the CUDA engine of this rank's GPU.
+    """
+
+    def __init__(self, comm=None, tracer=None, engine=None):
+        self.comm = comm or LocalComm()
+        if tracer is None:
+            if engine is None:
+                from .engine import default_engine
+                engine = default_engine()
+            tracer = lambda t, y, u, clip, keep_last: engine.trace(  # noqa: E731
+                t, y, u, clip=clip, keep_last=keep_last)
+        self.tracer = tracer
+
+    def local(self, a):
+        return shard(a, self.comm.rank, self.comm.world)
+
+    def spot(self, table, y0, u0, clip=False):
+        """full (N, 3) last-surface intercepts on every rank: each rank traces
+        its shard (keep-LAST), then one all-gather."""
+        n = len(y0)
+        Y, U, I, T = self.tracer(table, self.local(y0), self.local(u0), clip, True)
+        return self.comm.all_gather_rows(Y[0], n)
+
+    def rms(self, table, y0, u0, w=None, clip=False):
+        """GeometricTrace.rms of the whole bundle from per-rank moments
+        (two all-reduces of 8 doubles; no ray data crosses the link)."""
+        n = len(y0)
+        Y, U, I, T = self.tracer(table, self.local(y0), self.local(u0), clip, True)
+        y = Y[0][:, :2]
+        wl = np.full(len(y), 1.0/n) if w is None else self.local(np.asarray(w, float))
+        fin = np.isfinite(y).all(1)
+        m = self.comm.sum([fin.sum(), len(y), y[fin, 0].sum(), y[fin, 1].sum()])
+        if m[0] != m[1]:
+            return float("nan")            # the reference's rms is not NaN-masked
+        c = m[2:4]/m[1]
+        r = (wl*np.square(y - c).sum(1)).sum()
+        return float(np.sqrt(self.comm.sum([r])[0]))

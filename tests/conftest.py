@@ -43,7 +43,7 @@ def load_systems():
     return raw
 
 
-def assert_parity(got, want, rtol, what="", scale_floor=1.0):
+def assert_parity(got, want, rtol, what="", scale_floor=1.0, global_scale=False):
     """The comparator of SURVEY 8(d): identical NaN mask and
     |a-b| <= rtol*max(|b|, scale) with scale = max finite |b| of the array
     row (per surface) for lengths, 1 for direction cosines."""
@@ -59,6 +59,8 @@ def assert_parity(got, want, rtol, what="", scale_floor=1.0):
     # per-surface scale (axis 0 = surface)
     absw = np.where(fin, np.abs(want), 0.0)
     scale = absw.reshape(absw.shape[0], -1).max(1)
+    if global_scale:      # one scale for the whole trace (the lens's size)
+        scale = np.full_like(scale, scale.max())
     scale = np.maximum(scale, scale_floor).reshape((-1,) + (1,)*(want.ndim - 1))
     with np.errstate(invalid="ignore"):
         err = np.where(fin, np.abs(got - want)/np.maximum(np.abs(want), scale), 0.0)
