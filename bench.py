@@ -318,7 +318,7 @@ def main():
                        "wavelengths": nl, "parallelism": "rays sharded x%d" % world,
                        "arithmetic": "exact" if args.exact else "fast",
                        "stores": "direct" if args.direct else "tma-bulk",
-                       "rays_per_thread": args.rpt or int(os.environ.get("RTX_RPT", "1")),
+                       "kernel_config": "rpt=%s store=%s warps=%s nbuf=%s (0/unset: library default rpt 2, per-CTA TMA bulk stores, 16 warps, 1 staging buffer)" % (args.rpt, os.environ.get("RTX_STORE", "-"), os.environ.get("RTX_WARPS", "-"), os.environ.get("RTX_NBUF", "-")),
                        "l2": "outputs %.1f GB per launch >> 126 MB L2 (no flush needed)"
                              % (alg_bytes/1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

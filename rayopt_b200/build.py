@@ -41,6 +41,8 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     cmd = [nvcc()] + NVCC_FLAGS
+    if os.environ.get("RTX_TUNING_SPACE"):      # extra kernel variants for sweeps
+        cmd += ["-DRTX_TUNING_SPACE"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]

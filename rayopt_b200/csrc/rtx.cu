@@ -59,7 +59,13 @@ struct rtx_ctx {
     double* d_moments = nullptr;
     int64_t launches = 0;
     int max_smem_optin = 0;
-    int default_rpt = 1;
+    // kernel configuration (defaults = measured best, profiles/r1_sweep*.txt)
+    int default_rpt = 2;      // rays per thread
+    int store = 2;            // STORE_WARP / STORE_CTA
+    int warps = 16;           // warps per CTA
+    int nbuf = 1;             // staging buffers per CTA
+    int lockstep = 1;         // CTA barrier per stored surface (STORE_WARP)
+    int max_ctas_per_sm = 0;  // 0: whatever fits
 };
 
 namespace {
@@ -126,48 +132,72 @@ int ensure_slots(rtx_ctx* ctx, size_t bytes) {
     return 0;
 }
 
-template <typename T, bool EXACT, int RPT, bool BULK>
+template <typename T, bool EXACT, int RPT, int STORE, int WARPS, int NBUF>
 int launch_one(rtx_ctx* ctx, const TraceParams<T>& p, cudaStream_t stream) {
-    auto kern = trace_kernel<T, EXACT, RPT, BULK>;
-    size_t smem = trace_smem_bytes<T, RPT>(p.S, BULK);
+    auto kern = trace_kernel<T, EXACT, RPT, STORE, WARPS, NBUF>;
+    constexpr int threads = WARPS * 32;
+    size_t smem = trace_smem_bytes<T, RPT>(p.S, STORE, WARPS, NBUF);
     if ((int)smem > ctx->max_smem_optin) return RTX_E_UNSUPPORTED;
     if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     if (occ < 1) occ = 1;
-    const long long per_cta = (long long)THREADS * RPT;
+    if (ctx->max_ctas_per_sm > 0 && occ > ctx->max_ctas_per_sm) occ = ctx->max_ctas_per_sm;
+    const long long per_cta = (long long)threads * RPT;
     long long tiles = (p.N + per_cta - 1) / per_cta;
     long long grid = (long long)ctx->sm_count * occ;  // persistent: one wave
     if (grid > tiles) grid = tiles;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, THREADS, smem, stream>>>(p);
+    kern<<<(unsigned)grid, threads, smem, stream>>>(p);
     ctx->launches++;
     return (int)cudaGetLastError();
 }
 
+// the instantiated tuning space (rpt, store, warps, nbuf)
 template <typename T, bool EXACT>
-int launch_rpt(rtx_ctx* ctx, const TraceParams<T>& p, int rpt, bool bulk, cudaStream_t stream) {
-    if (!bulk) return launch_one<T, EXACT, 1, false>(ctx, p, stream);
-    if (rpt == 2) return launch_one<T, EXACT, 2, true>(ctx, p, stream);
-    return launch_one<T, EXACT, 1, true>(ctx, p, stream);
+int launch_cfg(rtx_ctx* ctx, const TraceParams<T>& p, int rpt, int store, int warps, int nbuf,
+               cudaStream_t stream) {
+#define RTX_CASE(R, ST, W, NB)                                  \
+    if (rpt == R && store == ST && warps == W && nbuf == NB)    \
+        return launch_one<T, EXACT, R, ST, W, NB>(ctx, p, stream);
+    if (store == STORE_DIRECT) return launch_one<T, EXACT, 1, STORE_DIRECT, 8, 1>(ctx, p, stream);
+    RTX_CASE(1, STORE_WARP, 8, 2)
+    RTX_CASE(2, STORE_WARP, 8, 2)
+    RTX_CASE(2, STORE_CTA, 16, 1)
+#ifdef RTX_TUNING_SPACE
+    RTX_CASE(2, STORE_CTA, 8, 1)
+    RTX_CASE(2, STORE_CTA, 8, 2)
+    RTX_CASE(1, STORE_WARP, 16, 2)
+    RTX_CASE(2, STORE_WARP, 8, 1)
+    RTX_CASE(1, STORE_CTA, 8, 1)
+    RTX_CASE(1, STORE_CTA, 8, 2)
+    RTX_CASE(1, STORE_CTA, 16, 1)
+    RTX_CASE(1, STORE_CTA, 16, 2)
+    RTX_CASE(2, STORE_CTA, 16, 2)
+    RTX_CASE(1, STORE_CTA, 32, 1)
+    RTX_CASE(1, STORE_CTA, 32, 2)
+    RTX_CASE(2, STORE_CTA, 32, 1)
+#endif
+#undef RTX_CASE
+    return RTX_E_UNSUPPORTED;
 }
 
 template <typename T>
-int launch_trace(rtx_ctx* ctx, const TraceParams<T>& p, bool exact, int rpt, bool bulk,
-                 cudaStream_t stream);
+int launch_trace(rtx_ctx* ctx, const TraceParams<T>& p, bool exact, int rpt, int store, int warps,
+                 int nbuf, cudaStream_t stream);
 
 template <>
 int launch_trace<double>(rtx_ctx* ctx, const TraceParams<double>& p, bool exact, int rpt,
-                         bool bulk, cudaStream_t stream) {
-    if (exact) return launch_rpt<double, true>(ctx, p, rpt, bulk, stream);
-    return launch_rpt<double, false>(ctx, p, rpt, bulk, stream);
+                         int store, int warps, int nbuf, cudaStream_t stream) {
+    if (exact) return launch_cfg<double, true>(ctx, p, rpt, store, warps, nbuf, stream);
+    return launch_cfg<double, false>(ctx, p, rpt, store, warps, nbuf, stream);
 }
 template <>
-int launch_trace<float>(rtx_ctx* ctx, const TraceParams<float>& p, bool exact, int rpt, bool bulk,
-                        cudaStream_t stream) {
+int launch_trace<float>(rtx_ctx* ctx, const TraceParams<float>& p, bool exact, int rpt, int store,
+                        int warps, int nbuf, cudaStream_t stream) {
     if (exact) return RTX_E_UNSUPPORTED;  // RTX_EXACT is FP64 only
-    return launch_rpt<float, false>(ctx, p, rpt, bulk, stream);
+    return launch_cfg<float, false>(ctx, p, rpt, store, warps, nbuf, stream);
 }
 
 // convert + upload the table; returns the device pointer.  The copy is
@@ -210,6 +240,7 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
     }
     TraceParams<T> p;
     memset(&p, 0, sizeof(p));
+    p.lockstep = 0;
     p.table = table;
     p.S = S;
     p.clip = clip ? 1 : 0;
@@ -229,10 +260,22 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
     int rpt = ctx->default_rpt;
     if (flags & RTX_RPT1) rpt = 1;
     if (flags & RTX_RPT2) rpt = 2;
-    if (N <= 32 * 1024) rpt = 1;  // small bundles: spread over more warps
-    bool bulk = !(flags & RTX_STORE_DIRECT) && (ld % (32 * rpt) == 0) && al16(Y) && al16(U) &&
-                al16(I) && al16(Tt);
-    return launch_trace<T>(ctx, p, (flags & RTX_EXACT) != 0, rpt, bulk, stream);
+    int store = ctx->store, warps = ctx->warps, nbuf = ctx->nbuf;
+    if (N <= 32 * 1024) {  // small bundles: spread over more warps
+        rpt = 1;
+        store = STORE_WARP;
+        warps = 8;
+        nbuf = 2;
+    } else if (rpt != ctx->default_rpt) {  // an explicit RPT request: its warp-bulk kernel
+        store = STORE_WARP;
+        warps = 8;
+        nbuf = 2;
+    }
+    const bool bulk_ok = !(flags & RTX_STORE_DIRECT) && (ld % (32 * rpt) == 0) && al16(Y) &&
+                         al16(U) && al16(I) && al16(Tt);
+    if (!bulk_ok) store = STORE_DIRECT;
+    p.lockstep = ctx->lockstep;
+    return launch_trace<T>(ctx, p, (flags & RTX_EXACT) != 0, rpt, store, warps, nbuf, stream);
 }
 
 int ensure_chunk(rtx_ctx* ctx, ChunkBuf& cb, size_t in_bytes, size_t out3, size_t out1) {
@@ -415,10 +458,25 @@ int rtx_init(int device, rtx_ctx** out) {
     CK(cudaEventCreate(&ctx->k0));
     CK(cudaEventCreate(&ctx->k1));
     CK(cudaMalloc((void**)&ctx->d_moments, 8 * sizeof(double)));
+    // tuning knobs (experiments; the defaults above are the measured best)
     if (const char* e = getenv("RTX_RPT")) {
         int v = atoi(e);
         if (v == 1 || v == 2) ctx->default_rpt = v;
     }
+    if (const char* e = getenv("RTX_WARPS")) {
+        int v = atoi(e);
+        if (v == 8 || v == 16 || v == 32) ctx->warps = v;
+    }
+    if (const char* e = getenv("RTX_STORE")) {
+        int v = atoi(e);
+        if (v == 1 || v == 2) ctx->store = v;
+    }
+    if (const char* e = getenv("RTX_NBUF")) {
+        int v = atoi(e);
+        if (v == 1 || v == 2) ctx->nbuf = v;
+    }
+    if (const char* e = getenv("RTX_LOCK")) ctx->lockstep = atoi(e) != 0;
+    if (const char* e = getenv("RTX_MAX_CTAS")) ctx->max_ctas_per_sm = atoi(e);
     *out = ctx;
     return 0;
 }

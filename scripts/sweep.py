@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Tuning sweep of the trace kernel on the C2 workload (one wavelength bundle
+per launch, 1e7 rays, S=12, FP64): env knobs RTX_RPT / RTX_WARPS / RTX_LOCK /
+RTX_MAX_CTAS are read by rtx_init, so one Engine per configuration.
+usage: python scripts/sweep.py [--rays N] [--exact 0|1] cfg1 cfg2 ...
+       cfg = rpt,store,warps,nbuf,lock,maxctas   e.g. 2,1,8,2,1,0
+       (store 1: per-warp bulk stores, 2: per-CTA bulk stores)
+Build with RTX_TUNING_SPACE=1 for the full variant space."""
+import argparse, json, os, statistics, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+from rayopt_b200.engine import Engine
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rays", type=int, default=10_000_000)
+ap.add_argument("--exact", type=int, default=0)
+ap.add_argument("--system", default="double_gauss")
+ap.add_argument("--dtype", default="f64")
+ap.add_argument("cfgs", nargs="*", default=["2,1,8,2,1,0"])
+a = ap.parse_args()
+ent = bench.load_system(a.system)
+S, N = ent["S"], a.rays
+dt = np.float64 if a.dtype == "f64" else np.float32
+w = np.dtype(dt).itemsize
+ld = ((N + 63)//64)*64
+mem = Engine(0)
+y0, u0 = bench.make_rays(ent, 0, N, 0)
+d_y0, d_u0 = mem.to_device(y0, dt), mem.to_device(u0, dt)
+Y, U, I = (mem.empty((S, ld, 3), dt) for _ in range(3))
+T = mem.empty((S, ld), dt)
+alg = N*(6*w + 10*w*S)
+for cfg in a.cfgs:
+    rpt, store, warps, nbuf, lock, maxc = (int(x) for x in cfg.split(","))
+    os.environ.update(RTX_RPT=str(rpt), RTX_STORE=str(store), RTX_WARPS=str(warps),
+                      RTX_NBUF=str(nbuf), RTX_LOCK=str(lock), RTX_MAX_CTAS=str(maxc))
+    e = Engine(0)
+    ms = []
+    try:
+        e.trace_device(ent["tables"][0], d_y0, d_u0, Y, U, I, T, N=N, ld=ld, clip=True, exact=bool(a.exact))
+    except Exception as ex:
+        print("cfg %s: %s" % (cfg, ex), flush=True)
+        e.close()
+        continue
+    for i in range(12):
+        e.trace_device(ent["tables"][0], d_y0, d_u0, Y, U, I, T, N=N, ld=ld, clip=True, exact=bool(a.exact))
+        t = e.last_kernel_ms()
+        if i >= 4:
+            ms.append(t)
+    m = statistics.median(ms)
+    print("rpt %d store %d warps %2d nbuf %d lock %d maxctas %d exact %d %s %s: %7.3f ms (min %.3f)  %7.1f GB/s  %.3e ray-surf/s  frac %.3f" % (
+        rpt, store, warps, nbuf, lock, maxc, a.exact, a.dtype, a.system, m, min(ms), alg/m/1e6, N*S/m*1e3, alg/m/1e6/6573.2), flush=True)
+    e.close()

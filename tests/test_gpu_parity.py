@@ -97,6 +97,22 @@ def test_fp32_vs_reference_golden(eng, name):
     assert flips <= max(2, c["y0"].shape[0]//100)*3*len(c["table"]), flips
 
 
+def test_store_paths_identical_large(eng, systems):
+    """per-CTA bulk stores (default), per-warp bulk stores (rpt 1, 2) and
+    per-thread stores give bit-identical arrays on a 70k-ray ragged bundle"""
+    ent = systems["zoom"]
+    table, aim = ent["tables"][1], ent["aim"][1][2]
+    y0, u0 = aim_infinite(aim["field"], disc(70001, 9), aim["z"], aim["p"], ent["object_angle"])
+    ref = eng.trace(table, y0, u0, clip=True, direct=True)
+    for rpt in (0, 1, 2):
+        got = eng.trace(table, y0, u0, clip=True, rpt=rpt)
+        for x, y in zip(got, ref):
+            assert np.array_equal(x, y, equal_nan=True), rpt
+    last = eng.trace(table, y0, u0, clip=True, keep_last=True)
+    for x, y in zip(last, ref):
+        assert np.array_equal(x[0], y[-1], equal_nan=True)
+
+
 @pytest.mark.parametrize("name", ["double_gauss_l0_clip", "cooke_asph_f07_clip",
                                   "tilted_clip1", "singlet_c1"])
 def test_store_paths_identical(eng, name):
@@ -159,13 +175,14 @@ def test_large_bundle_vs_oracle(eng, systems, sysname, n, clip):
                               ent["object_angle"])
         want = np_oracle.trace(table, y0, u0, clip=clip)
         newton = bool((table["n_asph"] >= 0).any())
-        got = eng.trace(table, y0, u0, clip=clip, exact=True, rpt=1 + li)
+        # default configuration: per-CTA TMA bulk stores (N > 32768), ragged tail
+        got = eng.trace(table, y0, u0, clip=clip, exact=True)
         for a, b, w in zip(got, want, "yuit"):
             if newton:
                 assert_parity(a, b, 1e-12, "%s exact %s" % (sysname, w))
             else:
                 assert np.array_equal(a, b, equal_nan=True), (sysname, w)
-        got = eng.trace(table, y0, u0, clip=clip, rpt=2 - li)
+        got = eng.trace(table, y0, u0, clip=clip, rpt=(0, 1, 2)[(li + len(sysname)) % 3])
         for a, b, w in zip(got, want, "yuit"):
             assert_parity(a, b, FP64_RTOL, "%s fast %s" % (sysname, w))
 
