@@ -66,6 +66,7 @@ struct rtx_ctx {
     int nbuf = 1;             // staging buffers per CTA
     int lockstep = 1;         // CTA barrier per stored surface (STORE_WARP)
     int max_ctas_per_sm = 0;  // 0: whatever fits
+    bool tuned = false;       // an RTX_* environment knob overrides the heuristics
 };
 
 namespace {
@@ -165,6 +166,8 @@ int launch_cfg(rtx_ctx* ctx, const TraceParams<T>& p, int rpt, int store, int wa
     RTX_CASE(1, STORE_WARP, 8, 2)
     RTX_CASE(2, STORE_WARP, 8, 2)
     RTX_CASE(2, STORE_CTA, 16, 1)
+    RTX_CASE(1, STORE_CTA, 16, 1)
+    RTX_CASE(2, STORE_CTA, 32, 1)
 #ifdef RTX_TUNING_SPACE
     RTX_CASE(2, STORE_CTA, 8, 1)
     RTX_CASE(2, STORE_CTA, 8, 2)
@@ -172,12 +175,10 @@ int launch_cfg(rtx_ctx* ctx, const TraceParams<T>& p, int rpt, int store, int wa
     RTX_CASE(2, STORE_WARP, 8, 1)
     RTX_CASE(1, STORE_CTA, 8, 1)
     RTX_CASE(1, STORE_CTA, 8, 2)
-    RTX_CASE(1, STORE_CTA, 16, 1)
     RTX_CASE(1, STORE_CTA, 16, 2)
     RTX_CASE(2, STORE_CTA, 16, 2)
     RTX_CASE(1, STORE_CTA, 32, 1)
     RTX_CASE(1, STORE_CTA, 32, 2)
-    RTX_CASE(2, STORE_CTA, 32, 1)
 #endif
 #undef RTX_CASE
     return RTX_E_UNSUPPORTED;
@@ -261,12 +262,26 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
     if (flags & RTX_RPT1) rpt = 1;
     if (flags & RTX_RPT2) rpt = 2;
     int store = ctx->store, warps = ctx->warps, nbuf = ctx->nbuf;
+    if (!ctx->tuned) {
+        // measured best configurations (profiles/r1_sweep5_configs.txt):
+        //  FP64: 16 warps x 2 rays, per-CTA bulk stores (24 KB runs)
+        //  FP32: 32 warps x 2 rays (24 KB runs again)
+        //  FP64 with Newton (aspheric) surfaces is FP64-pipe bound: 1 ray per
+        //  thread and two 16-warp CTAs per SM hide the long dependent chains
+        if (sizeof(T) == 4) {
+            warps = 32;
+        } else {
+            int newton = 0;
+            for (int i = 0; i < S; ++i) newton += surf && surf[i].n_asph >= 0;
+            if (rpt == ctx->default_rpt && newton * 4 >= S) rpt = 1;
+        }
+    }
     if (N <= 32 * 1024) {  // small bundles: spread over more warps
         rpt = 1;
         store = STORE_WARP;
         warps = 8;
         nbuf = 2;
-    } else if (rpt != ctx->default_rpt) {  // an explicit RPT request: its warp-bulk kernel
+    } else if ((flags & (RTX_RPT1 | RTX_RPT2))) {  // explicit RPT: its per-warp store kernel
         store = STORE_WARP;
         warps = 8;
         nbuf = 2;
@@ -462,6 +477,7 @@ int rtx_init(int device, rtx_ctx** out) {
     if (const char* e = getenv("RTX_RPT")) {
         int v = atoi(e);
         if (v == 1 || v == 2) ctx->default_rpt = v;
+        ctx->tuned = true;
     }
     if (const char* e = getenv("RTX_WARPS")) {
         int v = atoi(e);
@@ -475,6 +491,7 @@ int rtx_init(int device, rtx_ctx** out) {
         int v = atoi(e);
         if (v == 1 || v == 2) ctx->nbuf = v;
     }
+    if (getenv("RTX_WARPS") || getenv("RTX_STORE") || getenv("RTX_NBUF")) ctx->tuned = true;
     if (const char* e = getenv("RTX_LOCK")) ctx->lockstep = atoi(e) != 0;
     if (const char* e = getenv("RTX_MAX_CTAS")) ctx->max_ctas_per_sm = atoi(e);
     *out = ctx;

@@ -267,3 +267,14 @@ def test_round_trip_properties_full_size(eng, systems):
     assert_parity(got_y, want[0], FP64_RTOL, "1e7 sample y")
     for a in (Y, U, d_y0, d_u0):
         a.free()
+
+
+def test_sharded_trace_single_rank(eng):
+    """rayopt_b200.sharding on the CUDA engine (world of one); the two-rank
+    gloo variant of the same class runs on CPU in tests/test_sharding_gloo.py"""
+    from rayopt_b200.sharding import ShardedTrace
+    c = load_golden("double_gauss_f1_noclip")
+    st = ShardedTrace(engine=eng)
+    spot = st.spot(c["table"], c["y0"], c["u0"], clip=False)
+    assert_parity(spot[None], c["Y"][-1:], FP64_RTOL, "sharded spot")
+    assert abs(st.rms(c["table"], c["y0"], c["u0"]) - np_oracle.rms(c["Y"][-1])) < 1e-12
