@@ -5,8 +5,8 @@ Hot path only: ``GeometricTrace.propagate`` / ``System.propagate``
 CUDA (sm_100a) launch behind a C ABI (include/rtx.h).  No PyTorch, no CPU
 fallback: importing works anywhere, tracing needs librtx.so and a GPU.
 """
-from .surface_table import (SURFACE_DTYPE, pack_system, pack_element,  # noqa: F401
-                            table_from_json, table_to_json)
+from .surface_table import (SURFACE_DTYPE, PackedSystem, pack_system,  # noqa: F401
+                            pack_element, table_from_json, table_to_json)
 from .geometric_trace import (GeometricTrace, PropagateMixin, bind,  # noqa: F401
                               system_propagate, install)
 from .engine import Engine, DeviceArray, default_engine  # noqa: F401

@@ -50,18 +50,39 @@ class PropagateMixin:
             return a
         return np.empty(shape)
 
+    # For unrotated systems the incidence array is redundant: i[j] (direction
+    # arriving at surface j, system.py:461-463) is bit-for-bit u[j-1] (direction
+    # leaving surface j-1).  `u` and `i` are then two views of ONE (S+2, N, 3)
+    # buffer shifted by a row, the kernel does not store `i`, and a full trace
+    # moves 56 instead of 80 bytes per ray-surface over HBM and PCIe.  The
+    # first rotated element (or rotated start frame) switches to a real array.
+    alias_incidence = True
+
     def allocate(self, nrays):
         """rayopt/geometric_trace.py:37-47"""
         self.length = len(self.system)          # Trace.allocate, raytrace.py:29
         self.nrays = nrays
         self.n = np.empty(self.length)
         self.y = self._empty((self.length, nrays, 3))
-        self.u = self._empty((self.length, nrays, 3))
-        self.i = self._empty((self.length, nrays, 3))
+        if self.alias_incidence:
+            self._uext = self._empty((self.length + 1, nrays, 3))
+            self.u = self._uext[1:]
+            self.i = self._uext[:-1]
+            self._i_alias = True
+        else:
+            self.u = self._empty((self.length, nrays, 3))
+            self.i = self._empty((self.length, nrays, 3))
+            self._i_alias = False
         self.w = None
         self.ref = None
         self.l = 1.
         self.t = self._empty((self.length, nrays))
+
+    def _materialize_i(self):
+        i = self._empty((self.length, self.nrays, 3))
+        i[:] = self.i
+        self.i = i
+        self._i_alias = False
 
     def _cache_system(self):
         """Trace.propagate, rayopt/raytrace.py:32-36"""
@@ -83,15 +104,23 @@ class PropagateMixin:
             return
         sl = slice(start, start + rows)
         eng = self._engine()
+        alias = getattr(self, "_i_alias", False)
+        if alias and (rot0 is not None or (table["flags"] & 1).any()):
+            self._materialize_i()
+            alias = False
         if np.dtype(self.dtype) == np.float64:
+            out = {"y": self.y[sl], "u": self.u[sl], "t": self.t[sl]}
+            if not alias:
+                out["i"] = self.i[sl]
             eng.trace(table, self.y[init], self.u[init], clip=clip, rot0=rot0,
-                      exact=self.exact,
-                      out={"y": self.y[sl], "u": self.u[sl], "i": self.i[sl],
-                           "t": self.t[sl]})
+                      exact=self.exact, out=out, want=tuple(out))
         else:
+            want = ("y", "u", "t") if alias else ("y", "u", "i", "t")
             Y, U, I, T = eng.trace(table, self.y[init], self.u[init], clip=clip,
-                                   rot0=rot0, dtype=self.dtype)
-            self.y[sl], self.u[sl], self.i[sl], self.t[sl] = Y, U, I, T
+                                   rot0=rot0, dtype=self.dtype, want=want)
+            self.y[sl], self.u[sl], self.t[sl] = Y, U, T
+            if not alias:
+                self.i[sl] = I
         self.n[sl] = n
 
 
@@ -106,11 +135,13 @@ def _release(engine_ref, address):
 class GeometricTrace(PropagateMixin):
     """Standalone drop-in (no rayopt import needed)."""
 
-    def __init__(self, system, engine=None, dtype=np.float64, exact=False):
+    def __init__(self, system, engine=None, dtype=np.float64, exact=False,
+                 alias_incidence=True):
         self.system = system
         self.engine = engine
         self.dtype = dtype
         self.exact = exact
+        self.alias_incidence = alias_incidence
 
     def rays_given(self, y, u, l=None, w=None, ref=0):
         """rayopt/geometric_trace.py:49-70"""
@@ -201,7 +232,7 @@ def install(system_class, trace_class=None, engine=None, exact=False):
     if trace_class is not None:
         trace_class.allocate = PropagateMixin.allocate
         trace_class.propagate = PropagateMixin.propagate
-        for k in ("_engine", "_empty", "_cache_system"):
+        for k in ("_engine", "_empty", "_cache_system", "_materialize_i", "alias_incidence"):
             setattr(trace_class, k, getattr(PropagateMixin, k))
         trace_class.engine = engine
         trace_class.dtype = np.float64

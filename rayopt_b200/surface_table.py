@@ -110,6 +110,8 @@ def pack_system(system, l, start=1, stop=None, n0=None):
     ``GeometricTrace.n[start:stop]``) and the 3x3 ``rot_normal`` of
     ``system[start-1]`` or None (geometric_trace.py:76).
     """
+    if hasattr(system, "pack"):                # pre-packed (PackedSystem)
+        return system.pack(l, start, stop, n0)
     elements = list(system[start:stop])
     if len(elements) > RTX_MAX_SURFACES:
         raise ValueError("too many surfaces: %d" % len(elements))
@@ -125,6 +127,36 @@ def pack_system(system, l, start=1, stop=None, n0=None):
     if getattr(init, "rotated", False):
         rot0 = np.ascontiguousarray(init.rot_normal, float)
     return table, n, rot0
+
+
+class PackedSystem:
+    """A lens given directly as packed tables, one per wavelength -- what
+    ``pack_system`` would produce from a rayopt ``System``.  Lets
+    ``GeometricTrace`` run where rayopt itself is not installed (the GPU
+    benchmark box) and skips the per-call walk over the elements."""
+
+    def __init__(self, wavelengths, tables, n_before_first):
+        self.wavelengths = [float(l) for l in wavelengths]
+        self._tables = {float(l): np.ascontiguousarray(t, SURFACE_DTYPE)
+                        for l, t in zip(wavelengths, tables)}
+        self._n0 = {float(l): float(n) for l, n in zip(wavelengths, n_before_first)}
+        self._len = len(tables[0]) + 1
+
+    def __len__(self):
+        return self._len
+
+    def refractive_index(self, l, i):
+        t = self._tables[float(l)]
+        return self._n0[float(l)] if i == 0 else float(t["n"][i - 1])
+
+    def pack(self, l, start=1, stop=None, n0=None):
+        full = self._tables[float(l)]
+        idx = range(self._len)[start:stop]
+        table = full[idx.start - 1:idx.stop - 1].copy() if len(idx) else full[:0].copy()
+        rot0 = None
+        if start >= 2 and full["flags"][start - 2] & F_ROTATED:
+            rot0 = full["rot"][start - 2].reshape(3, 3).copy()
+        return table, table["n"].copy(), rot0
 
 
 def table_to_json(table):

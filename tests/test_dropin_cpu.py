@@ -1,0 +1,127 @@
+"""Host logic of the GeometricTrace drop-in on CPU: the engine is replaced by
+a stand-in that runs the oracle through the same `Engine.trace` interface, so
+that allocation, the u/i aliasing, sub-range propagate, rms/refocus and the
+binding into the reference classes are exercised without a GPU."""
+import warnings
+
+import numpy as np
+import pytest
+import yaml
+
+import np_oracle
+import ref_shim
+import systems_yaml
+from conftest import load_golden, load_systems
+from rayopt_b200 import GeometricTrace, PackedSystem, bind, system_propagate
+
+
+class OracleEngine:
+    """same call surface as rayopt_b200.engine.Engine.trace"""
+    calls = 0
+
+    def trace(self, table, y0, u0, clip=False, keep_last=False, rot0=None, dtype=np.float64,
+              exact=False, direct=False, rpt=0, out=None, want=("y", "u", "i", "t")):
+        OracleEngine.calls += 1
+        Y, U, I, T = np_oracle.trace(table, y0, u0, clip=clip, rot0=rot0)
+        res = dict(y=Y, u=U, i=I, t=T)
+        if out is None:
+            return tuple(res[k] if k in want else None for k in "yuit")
+        for k in want:
+            out[k][...] = res[k]
+        return tuple(out.get(k) for k in "yuit")
+
+    def pinned_empty(self, shape, dtype):
+        return np.empty(shape, dtype)
+
+
+def _packed(name):
+    ent = load_systems()[name]
+    return PackedSystem(ent["wavelengths"], ent["tables"], [n[0] for n in ent["n"]]), ent
+
+
+def test_alias_incidence_full_and_subrange():
+    ps, ent = _packed("double_gauss")
+    c = load_golden("double_gauss_l1_clip")
+    g = GeometricTrace(ps, engine=OracleEngine())
+    g.rays_given(c["y0"], c["u0"], l=ent["wavelengths"][1])
+    g.propagate(clip=True)
+    assert g._i_alias and np.shares_memory(g.i, g.u)
+    for a, b in ((g.y, c["Y"]), (g.u, c["U"]), (g.i, c["I"]), (g.t, c["T"])):
+        assert np.array_equal(a[1:], b, equal_nan=True)
+    assert np.array_equal(g.n[1:], c["n"]) and np.array_equal(g.i[0], g.u[0])
+    # propagate(start, stop) on a sub-range (geometric_trace.py:72-80)
+    c2 = load_golden("double_gauss_sub_4_9")
+    g.rays_given(c2["y0"]*0 + c["y0"][:1], c["u0"][:1], l=ent["wavelengths"][0])
+    g = GeometricTrace(ps, engine=OracleEngine())
+    g.allocate(c2["y0"].shape[0])
+    g.l, g.w, g.ref = ent["wavelengths"][0], None, 0
+    g.y[3], g.u[3], g.n[3] = c2["y0"], c2["u0"], c2["table"]["n0"][0]
+    g.propagate(start=4, stop=9, clip=True)
+    for a, b in ((g.y, c2["Y"]), (g.u, c2["U"]), (g.i, c2["I"]), (g.t, c2["T"])):
+        assert np.array_equal(a[4:9], b, equal_nan=True)
+
+
+def test_rotated_system_materialises_incidence():
+    c = load_golden("tilted_clip1")
+    ps = PackedSystem([587.56e-9], [c["table"]], [c["table"]["n0"][0]])
+    g = GeometricTrace(ps, engine=OracleEngine())
+    g.rays_given(c["y0"], c["u0"], l=587.56e-9)
+    g.propagate(clip=True)
+    assert not g._i_alias and not np.shares_memory(g.i, g.u)
+    for a, b in ((g.y, c["Y"]), (g.u, c["U"]), (g.i, c["I"]), (g.t, c["T"])):
+        assert np.array_equal(a[1:], b, equal_nan=True)
+    # without aliasing: same answer
+    g2 = GeometricTrace(ps, engine=OracleEngine(), alias_incidence=False)
+    g2.rays_given(c["y0"], c["u0"], l=587.56e-9)
+    g2.propagate(clip=True)
+    assert np.array_equal(g2.i, g.i, equal_nan=True)
+
+
+def test_rays_given_pads_2d_input_and_rms_known_answer():
+    """rays_given semantics (geometric_trace.py:49-70) and the reference's
+    known answer rms = 0.052 (test_raytrace.py:192-195)"""
+    ps, ent = _packed("cooke")
+    c = load_golden("cooke_radau13")
+    g = GeometricTrace(ps, engine=OracleEngine())
+    g.rays_given(c["y0"][:, :2], c["u0"][:, :2], w=c["w"])
+    assert g.l == ent["wavelengths"][0]
+    np.testing.assert_allclose(g.u[0, :, 2], c["u0"][:, 2], rtol=1e-15)
+    assert np.all(g.y[0, :, 2] == 0) and np.all(g.t[0] == 0)
+    g.propagate()
+    assert abs(g.rms() - 0.052)/0.052 < 1e-2
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+def test_bound_reference_class_matches_reference():
+    """rayopt_b200.bind(rayopt.GeometricTrace): rays_point / rays_clipping /
+    refocus of the REFERENCE class run on the replaced allocate/propagate and
+    give the reference's own results; System.propagate's replacement feeds
+    the reference's ray aiming."""
+    warnings.simplefilter("ignore")
+    R = ref_shim.load()
+    s = R.System(**yaml.safe_load(systems_yaml.COOKE))
+    s.update()
+    s.paraxial.refocus()
+    GT = bind(R.GeometricTrace, engine=OracleEngine())
+    ref = R.GeometricTrace(s)
+    ref.rays_point((0, 1.), nrays=300, distribution="hexapolar", clip=True)
+    got = GT(s)
+    got.rays_point((0, 1.), nrays=300, distribution="hexapolar", clip=True)
+    for k in "yuit":
+        assert np.array_equal(getattr(got, k), getattr(ref, k), equal_nan=True), k
+    assert np.array_equal(got.n, ref.n)
+    assert np.array_equal(got.path, ref.path) and np.array_equal(got.origins, ref.origins)
+    ref2, got2 = R.GeometricTrace(s), GT(s)
+    ref2.rays_clipping((0, 1.))
+    got2.rays_clipping((0, 1.))
+    assert np.array_equal(got2.y, ref2.y, equal_nan=True)
+    # the System.propagate cut used by aim_chief / aim_marginal (system.py:507-555)
+    y, u = s.aim((0, .5), None, *s.pupil((0, .5)), filter=False)
+    n0 = s.refractive_index(s.wavelengths[0], 0)
+    a = list(s.propagate(y, u, n0, s.wavelengths[0], stop=6, clip=False))
+    b = list(system_propagate(s, y, u, n0, s.wavelengths[0], stop=6, clip=False,
+                              engine=OracleEngine()))
+    assert len(a) == len(b) == 5
+    for ya, yb in zip(a, b):
+        for xa, xb in zip(ya, yb):
+            assert np.array_equal(np.asarray(xa), np.asarray(xb), equal_nan=True)
