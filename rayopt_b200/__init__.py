@@ -10,6 +10,7 @@ from .surface_table import (SURFACE_DTYPE, PackedSystem, pack_system,  # noqa: F
 from .geometric_trace import (GeometricTrace, PropagateMixin, bind,  # noqa: F401
                               system_propagate, install)
 from .engine import Engine, DeviceArray, default_engine  # noqa: F401
+from . import elements  # noqa: F401
 from ._lib import RtxError  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,0 +1,44 @@
+#!/bin/bash
+# compute-sanitizer passes over the store paths (small problem sizes), and the small-N latency
+mkdir -p gpurun_out
+cat > /tmp/san.py <<'PY'
+import sys, numpy as np
+sys.path.insert(0, "."); sys.path.insert(0, "tests"); sys.path.insert(0, "oracle")
+from conftest import load_golden, load_systems
+from rayopt_b200.engine import Engine
+from rayopt_b200.rays import aim_infinite, disc
+eng = Engine(0)
+ent = load_systems()["zoom"]
+table, aim = ent["tables"][0], ent["aim"][0][2]
+y0, u0 = aim_infinite(aim["field"], disc(40001, 1), aim["z"], aim["p"], ent["object_angle"])
+ref = eng.trace(table, y0, u0, clip=True, direct=True)
+for kw in (dict(), dict(rpt=1), dict(rpt=2), dict(exact=True), dict(dtype=np.float32), dict(keep_last=True)):
+    out = eng.trace(table, y0, u0, clip=True, **kw)
+    print(kw, out[0].shape, flush=True)
+c = load_golden("cooke_asph_f07_clip")
+eng.trace(c["table"], c["y0"], c["u0"], clip=True)
+c = load_golden("tilted_clip1")
+eng.trace(c["table"], c["y0"], c["u0"], clip=True, rot0=c["rot0"])
+eng.close()
+print("done")
+PY
+for tool in memcheck racecheck synccheck; do
+  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san.py > gpurun_out/sanitizer_$tool.txt 2>&1
+  echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|done" gpurun_out/sanitizer_$tool.txt | tail -3
+done
+python - <<'PY' > gpurun_out/latency.txt 2>&1
+import sys, time, numpy as np
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+from conftest import load_golden
+from rayopt_b200.engine import Engine
+eng = Engine(0)
+c = load_golden("cooke_single_ray")
+for n in (1, 3, 13, 1000):
+    y = np.repeat(c["y0"], n, 0); u = np.repeat(c["u0"], n, 0)
+    for _ in range(20): eng.trace(c["table"], y, u)
+    t0 = time.perf_counter()
+    for _ in range(500): eng.trace(c["table"], y, u)
+    print("N=%5d rays, S=8: %.1f us per GeometricTrace-style host-buffer trace call" % (n, (time.perf_counter()-t0)/500*1e6))
+PY
+cat gpurun_out/latency.txt
+free -g | head -2; nproc

@@ -278,3 +278,40 @@ def test_sharded_trace_single_rank(eng):
     spot = st.spot(c["table"], c["y0"], c["u0"], clip=False)
     assert_parity(spot[None], c["Y"][-1:], FP64_RTOL, "sharded spot")
     assert abs(st.rms(c["table"], c["y0"], c["u0"]) - np_oracle.rms(c["Y"][-1])) < 1e-12
+
+
+def test_element_level_entry_points(eng):
+    """rayopt_b200.elements.{propagate,intercept,refract} on the CUDA engine
+    against the oracle's single-surface functions (elements.py:306-315 etc.)"""
+    from rayopt_b200 import elements as el
+    c = load_golden("conics_clip1")
+    rec = c["table"][1]
+
+    class E:
+        curvature, conic = float(rec["c"]), float(rec["k"])
+        aspherics, alternate_intersection = None, False
+        radius = float(np.sqrt(rec["radius2"]))
+
+        def get_n_mu(self, n0, l):
+            return float(rec["n"]), n0/float(rec["n"])
+    rng = np.random.default_rng(2)
+    y0 = np.c_[rng.uniform(-3, 3, (500, 2)), -np.ones(500)]
+    u0 = rng.normal(0, .1, (500, 2))
+    u0 = np.c_[u0, np.sqrt(1 - np.square(u0).sum(1))]
+    n0 = float(rec["n0"])
+    one = np.zeros(1, c["table"].dtype)
+    from rayopt_b200.surface_table import pack_element
+
+    class Bare(E):
+        offset, rotated = (0., 0., 0.), False
+    pack_element(one[0], Bare(), n0, None)
+    wy, wu, wt = np_oracle.propagate_surface(one[0], y0, u0, True)
+    y, u, n, t = el.propagate(E(), y0, u0, n0, None, clip=True, engine=eng, exact=True)
+    assert n == float(rec["n"])
+    for a, b in ((y, wy), (u, wu), (t, wt)):
+        assert np.array_equal(a, b, equal_nan=True)
+    s = el.intercept(E(), y0, u0, engine=eng, exact=True)
+    assert np.array_equal(s, np_oracle.intercept(one[0], y0, u0), equal_nan=True)
+    on = np.isfinite(wy[:, 0])
+    r = el.refract(E(), wy[on], u0[on], float(one["mu"][0]), engine=eng)
+    assert_parity(r[None], np_oracle.refract(one[0], wy[on], u0[on])[None], FP64_RTOL, "refract")
