@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 cat > /tmp/san.py <<'PY'
 import sys, numpy as np
-sys.path.insert(0, "."); sys.path.insert(0, "tests"); sys.path.insert(0, "oracle")
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
 from conftest import load_golden, load_systems
 from rayopt_b200.engine import Engine
 from rayopt_b200.rays import aim_infinite, disc

@@ -6,7 +6,7 @@ launch, 160 GB of results in HBM).  The 1e8-ray bundle is ten copies of a
 the host generation time)."""
 import json, os, statistics, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import bench, np_oracle
 from rayopt_b200.engine import Engine

@@ -2,10 +2,10 @@
 """Run under torchrun on N GPUs: ray-sharded trace + NCCL all-gather of the
 last-surface intercepts and all-reduced rms, checked against the oracle.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port 29533 scripts/multi_gpu_check.py"""
+        --master-port 29533 tests/gpu_scripts/multi_gpu_check.py"""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import torch, torch.distributed as dist
