@@ -197,6 +197,33 @@ int rtx_trace_host(rtx_ctx *ctx, const rtx_surface *surf, int S,
                    const void *y0, const void *u0, int clip, int keep,
                    void *Y, void *U, void *I, void *T, unsigned flags);
 
+/* ---- fused trace + gather over peer memory (multi-GPU) ------- */
+/*
+ * Cross-process device memory: export a buffer of this context's GPU as an
+ * opaque 64-byte handle (cudaIpcGetMemHandle), open a handle exported by
+ * another process of the same node (peer access over NVLink is enabled
+ * lazily), close it again.
+ */
+#define RTX_IPC_HANDLE_BYTES 64
+int rtx_ipc_export(rtx_ctx *ctx, void *dptr, unsigned char *handle);
+int rtx_ipc_open(rtx_ctx *ctx, const unsigned char *handle, void **dptr);
+int rtx_ipc_close(rtx_ctx *ctx, void *dptr);
+/*
+ * Trace this rank's shard (N rays, DEVICE y0,u0) and store the LAST surface's
+ * intercepts straight into `npeers` (<= 8) gather buffers dst[k] -- (Ntotal_pad, 3)
+ * arrays of `dtype` that are local or peer-GPU memory (rtx_ipc_open) -- at ray
+ * offset dst_offset: the all-gather of GeometricTrace.y[-1] is done by the
+ * trace kernel's own TMA bulk stores over NVLink instead of a separate
+ * collective.  dst_offset must be a multiple of 64 rays and every buffer
+ * must hold dst_offset + N rounded up to 64 rays (whole 64-ray groups are
+ * written).  Asynchronous on the context stream; after rtx_sync on every
+ * rank and a cross-rank barrier all buffers hold the full spot.
+ */
+int rtx_trace_gather(rtx_ctx *ctx, const rtx_surface *surf, int S,
+                     const double *rot0, int dtype, int64_t N, const void *y0,
+                     const void *u0, int clip, int npeers, void *const *dst,
+                     int64_t dst_offset, unsigned flags);
+
 /* ---- self-test --------------------------------------------------------- */
 /*
  * The kernels use their own branch-free FP64 division / sqrt / rsqrt (the

@@ -230,11 +230,18 @@ int check_table(const rtx_surface* surf, int S) {
     return 0;
 }
 
+struct PeerDst {
+    int n = 0;
+    long long off = 0;
+    void* ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
 template <typename T>
 int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0, long long N,
                  const void* y0, const void* u0, int clip, int keep, long long ld, void* Y,
                  void* U, void* I, void* Tt, unsigned flags, cudaStream_t stream,
-                 const DevSurf<T>* table /* may be null: upload */) {
+                 const DevSurf<T>* table /* may be null: upload */,
+                 const PeerDst* peers = nullptr) {
     if (!table) {
         int rc = upload_table<T>(ctx, surf, S, stream, &table);
         if (rc) return rc;
@@ -257,6 +264,16 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
     p.U = (T*)U;
     p.I = (T*)I;
     p.Tt = (T*)Tt;
+    bool peers_ok = true;
+    if (peers && peers->n > 0) {
+        p.npeer = peers->n;
+        p.peer_off = peers->off;
+        for (int k = 0; k < peers->n; ++k) p.peer[k] = (T*)peers->ptr[k];
+        // bulk stores need 16-byte aligned runs in every destination
+        peers_ok = (peers->off * 3 * (long long)sizeof(T)) % 16 == 0;
+        for (int k = 0; k < peers->n; ++k)
+            peers_ok = peers_ok && (reinterpret_cast<uintptr_t>(peers->ptr[k]) & 15u) == 0;
+    }
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     int rpt = ctx->default_rpt;
     if (flags & RTX_RPT1) rpt = 1;
@@ -287,7 +304,7 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
         nbuf = 2;
     }
     const bool bulk_ok = !(flags & RTX_STORE_DIRECT) && (ld % (32 * rpt) == 0) && al16(Y) &&
-                         al16(U) && al16(I) && al16(Tt);
+                         al16(U) && al16(I) && al16(Tt) && peers_ok;
     if (!bulk_ok) store = STORE_DIRECT;
     p.lockstep = ctx->lockstep;
     return launch_trace<T>(ctx, p, (flags & RTX_EXACT) != 0, rpt, store, warps, nbuf, stream);
@@ -658,6 +675,62 @@ int rtx_trace_host(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* r
     if (dtype == RTX_F64)
         return trace_host<double>(ctx, surf, S, rot0, N, y0, u0, clip, keep, Y, U, I, T, flags);
     return trace_host<float>(ctx, surf, S, rot0, N, y0, u0, clip, keep, Y, U, I, T, flags);
+}
+
+int rtx_ipc_export(rtx_ctx* ctx, void* dptr, unsigned char* handle) {
+    if (!ctx || !dptr || !handle) return RTX_E_BADARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == RTX_IPC_HANDLE_BYTES, "ipc handle size");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle, &h, sizeof(h));
+    return 0;
+}
+int rtx_ipc_open(rtx_ctx* ctx, const unsigned char* handle, void** dptr) {
+    if (!ctx || !dptr || !handle) return RTX_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    CK(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int rtx_ipc_close(rtx_ctx* ctx, void* dptr) {
+    if (!ctx) return RTX_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaIpcCloseMemHandle(dptr));
+    return 0;
+}
+
+int rtx_trace_gather(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0, int dtype,
+                     int64_t N, const void* y0, const void* u0, int clip, int npeers,
+                     void* const* dst, int64_t dst_offset, unsigned flags) {
+    if (!ctx) return RTX_E_BADARG;
+    int rc = check_table(surf, S);
+    if (rc) return rc;
+    if (N < 0 || !y0 || !u0 || npeers < 1 || npeers > 8 || !dst || dst_offset < 0)
+        return RTX_E_BADARG;
+    if (dtype != RTX_F64 && dtype != RTX_F32) return RTX_E_BADARG;
+    if (N == 0) return 0;
+    PeerDst pd;
+    pd.n = npeers;
+    pd.off = dst_offset;
+    for (int k = 0; k < npeers; ++k) {
+        if (!dst[k]) return RTX_E_BADARG;
+        pd.ptr[k] = dst[k];
+    }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->k0, ctx->stream));
+    const long long ld = ((N + 63) / 64) * 64;  // only the gather destinations are written
+    if (dtype == RTX_F64)
+        rc = trace_device<double>(ctx, surf, S, rot0, N, y0, u0, clip, RTX_KEEP_LAST, ld, nullptr,
+                                  nullptr, nullptr, nullptr, flags, ctx->stream, nullptr, &pd);
+    else
+        rc = trace_device<float>(ctx, surf, S, rot0, N, y0, u0, clip, RTX_KEEP_LAST, ld, nullptr,
+                                 nullptr, nullptr, nullptr, flags, ctx->stream, nullptr, &pd);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->k1, ctx->stream));
+    ctx->kernel_timed = true;
+    return 0;
 }
 
 int rtx_selftest_math(rtx_ctx* ctx, int64_t n, const double* a, const double* b, double* out) {

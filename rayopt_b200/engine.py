@@ -221,6 +221,34 @@ class Engine:
             self._flags(exact, direct, rpt)))
         return tuple(res)
 
+    def trace_gather(self, table, y0, u0, dst_ptrs, dst_offset, N=None, clip=False,
+                     rot0=None, exact=False):
+        """rtx_trace_gather: trace the local shard (DEVICE y0,u0) and bulk-store
+        the last surface's intercepts into every buffer of `dst_ptrs` (raw
+        device pointers: local or peer memory) at ray offset `dst_offset`."""
+        table = self._table(table)
+        N = y0.shape[0] if N is None else int(N)
+        r0 = None if rot0 is None else np.ascontiguousarray(rot0, np.float64).reshape(9)
+        arr = (C.c_void_p*len(dst_ptrs))(*[C.c_void_p(int(p)) for p in dst_ptrs])
+        check(self.lib.rtx_trace_gather(
+            self.ctx, ptr(table), len(table), ptr(r0), _code(y0.dtype), N, y0.ptr, u0.ptr,
+            int(bool(clip)), len(dst_ptrs), C.cast(arr, C.c_void_p), int(dst_offset),
+            self._flags(exact, False)))
+
+    def ipc_export(self, darray):
+        h = (C.c_ubyte*64)()
+        check(self.lib.rtx_ipc_export(self.ctx, darray.ptr, C.cast(h, C.c_void_p)))
+        return bytes(h)
+
+    def ipc_open(self, handle):
+        h = (C.c_ubyte*64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        check(self.lib.rtx_ipc_open(self.ctx, C.cast(h, C.c_void_p), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, p):
+        check(self.lib.rtx_ipc_close(self.ctx, p))
+
     def selftest_math(self, a, b):
         """(6, n): engine a/b, IEEE a/b, engine sqrt(a), IEEE sqrt(a),
         engine 1/sqrt(a), IEEE 1/sqrt(a)"""

@@ -17,13 +17,15 @@ injected so that the host logic is testable on CPU with gloo.
 import numpy as np
 
 
-def bounds(n, world):
-    """contiguous shard boundaries: rank r owns [b[r], b[r+1])"""
-    return [(r*n)//world for r in range(world + 1)]
+def bounds(n, world, align=1):
+    """contiguous shard boundaries: rank r owns [b[r], b[r+1]); interior
+    boundaries are multiples of `align` rays"""
+    b = [((r*n)//world)//align*align for r in range(world)] + [n]
+    return b
 
 
-def shard(a, rank, world):
-    b = bounds(len(a), world)
+def shard(a, rank, world, align=1):
+    b = bounds(len(a), world, align)
     return a[b[rank]:b[rank + 1]]
 
 
@@ -127,3 +129,58 @@ class ShardedTrace:
         c = m[2:4]/m[1]
         r = (wl*np.square(y - c).sum(1)).sum()
         return float(np.sqrt(self.comm.sum([r])[0]))
+
+
+class PeerGather:
+    """Fused trace + all-gather over NVLink peer memory (rtx_trace_gather).
+
+    Every rank owns a (Npad, 3) gather buffer on its GPU, exports it through
+    CUDA IPC, and opens the buffers of all peers.  ``spot()`` then runs ONE
+    kernel per rank whose last-surface TMA bulk stores go straight into all
+    `world` buffers -- no separate collective, the transfer overlaps the
+    march tile by tile.  torch.distributed only carries the 64-byte handles
+    and the final barrier."""
+
+    ALIGN = 64
+
+    def __init__(self, engine, dist, n_total, dtype=np.float64):
+        self.eng, self.dist = engine, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        if self.world > 8:
+            raise ValueError("at most 8 peers (one NVSwitch box)")
+        self.n = int(n_total)
+        self.npad = (self.n + self.ALIGN - 1)//self.ALIGN*self.ALIGN + self.ALIGN
+        self.buf = engine.empty((self.npad, 3), dtype)
+        handles = [None]*self.world
+        dist.all_gather_object(handles, engine.ipc_export(self.buf))
+        self._opened = []
+        self.ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self.buf.ptr)
+            else:
+                p = engine.ipc_open(h)
+                self._opened.append(p)
+                self.ptrs.append(p)
+        self.b = bounds(self.n, self.world, self.ALIGN)
+
+    def local(self, a):
+        return a[self.b[self.rank]:self.b[self.rank + 1]]
+
+    def spot(self, table, y0_local_dev, u0_local_dev, clip=False, exact=False):
+        """full last-surface intercepts (n_total, 3) in this rank's device
+        buffer; returns it as a host array"""
+        n_local = self.b[self.rank + 1] - self.b[self.rank]
+        if n_local:
+            self.eng.trace_gather(table, y0_local_dev, u0_local_dev, self.ptrs,
+                                  self.b[self.rank], N=n_local, clip=clip, exact=exact)
+        self.eng.sync()
+        self.dist.barrier()          # every rank's stores have landed everywhere
+        return self.buf.download()[:self.n]
+
+    def close(self):
+        self.dist.barrier()
+        for p in self._opened:
+            self.eng.ipc_close(p)
+        self._opened = []
+        self.buf.free()

@@ -315,3 +315,30 @@ def test_element_level_entry_points(eng):
     on = np.isfinite(wy[:, 0])
     r = el.refract(E(), wy[on], u0[on], float(one["mu"][0]), engine=eng)
     assert_parity(r[None], np_oracle.refract(one[0], wy[on], u0[on])[None], FP64_RTOL, "refract")
+
+
+@pytest.mark.parametrize("n", [70001, 3000])
+def test_trace_gather_epilogue(eng, systems, n):
+    """rtx_trace_gather: the last surface's intercepts are bulk-stored by the
+    trace kernel itself into several gather buffers at a ray offset (here two
+    local buffers stand in for peer GPUs; the 2-GPU NVLink run is
+    tests/gpu_scripts/multi_gpu_check.py)"""
+    ent = systems["double_gauss"]
+    table, aim = ent["tables"][0], ent["aim"][0][3]
+    y0, u0 = aim_infinite(aim["field"], disc(n, 4), aim["z"], aim["p"], ent["object_angle"])
+    ref = eng.trace(table, y0, u0, clip=True, keep_last=True, want=("y",))[0][0]
+    off = 192
+    npad = (off + n + 63)//64*64 + 64
+    bufs = [eng.empty((npad, 3)) for _ in range(2)]
+    for b in bufs:
+        eng.lib.rtx_memset(eng.ctx, b.ptr, 0xff, b.nbytes)
+    d_y0, d_u0 = eng.to_device(y0), eng.to_device(u0)
+    eng.trace_gather(table, d_y0, d_u0, [b.ptr for b in bufs], off, clip=True)
+    eng.sync()
+    for b in bufs:
+        h = b.download()
+        assert np.array_equal(h[off:off + n], ref, equal_nan=True)
+        assert np.isnan(h[:off]).all()            # nothing written in front of the shard
+        b.free()
+    d_y0.free()
+    d_u0.free()
