@@ -250,6 +250,19 @@ int rtx_selftest_math(rtx_ctx *ctx, int64_t n, const double *a, const double *b,
 int rtx_moments(rtx_ctx *ctx, int dtype, int64_t N, const void *y,
                 const void *w, const double *center, double *m);
 
+/*
+ * Moments for GeometricTrace.refocus (rayopt/geometric_trace.py:82-99) on
+ * DEVICE arrays of one surface: y = intercepts (N,3), inc = incidence
+ * directions (N,3); u = inc_xy/inc_z (tanarcsin); rays with non-finite u are
+ * skipped.  About `center` = (y_x, y_y, u_x, u_y) (host, or NULL = 0):
+ * m[0]=#good, m[1]=#total, m[2..3]=sum dy, m[4..5]=sum du,
+ * m[6]=sum w (dy.du), m[7]=sum w (du.du).  The focus shift is
+ * -m[6]/m[7] taken about the means of the good rays (two calls).
+ */
+int rtx_focus_moments(rtx_ctx *ctx, int dtype, int64_t N, const void *y,
+                      const void *inc, const void *w, const double *center,
+                      double *m);
+
 #ifdef __cplusplus
 }
 #endif

@@ -779,4 +779,34 @@ int rtx_moments(rtx_ctx* ctx, int dtype, int64_t N, const void* y, const void* w
     return 0;
 }
 
+int rtx_focus_moments(rtx_ctx* ctx, int dtype, int64_t N, const void* y, const void* inc,
+                      const void* w, const double* center, double* m) {
+    if (!ctx || !y || !inc || !m || N < 0) return RTX_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    double c[4] = {0, 0, 0, 0};
+    if (center)
+        for (int k = 0; k < 4; ++k) c[k] = center[k];
+    CK(cudaMemsetAsync(ctx->d_moments, 0, 8 * sizeof(double), ctx->stream));
+    if (N > 0) {
+        long long blocks = (N + 255) / 256;
+        long long cap = (long long)ctx->sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        if (dtype == RTX_F64)
+            focus_moments_kernel<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+                (const double*)y, (const double*)inc, (const double*)w, N, c[0], c[1], c[2], c[3],
+                ctx->d_moments);
+        else if (dtype == RTX_F32)
+            focus_moments_kernel<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+                (const float*)y, (const float*)inc, (const float*)w, N, c[0], c[1], c[2], c[3],
+                ctx->d_moments);
+        else
+            return RTX_E_BADARG;
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(m, ctx->d_moments, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 }  // extern "C"

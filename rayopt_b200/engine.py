@@ -287,6 +287,27 @@ class Engine:
         return float(np.sqrt(m[3]))
 
 
+    def refocus_shift(self, y, inc, w=None, N=None, comm_sum=None):
+        """The focus shift of GeometricTrace.refocus (rayopt/geometric_trace.py:
+        82-99), t = -<w y, u>/<w u, u> about the means of the finite rays, from
+        DEVICE arrays y (N,3) and inc (N,3) of the surface -- no D2H of the rays.
+        `comm_sum` all-reduces the 8 moments for ray-sharded bundles."""
+        red = comm_sum or (lambda v: v)
+        N = y.shape[-2] if N is None else int(N)
+
+        def mom(center):
+            m = np.zeros(8)
+            c = None if center is None else np.ascontiguousarray(center, np.float64)
+            check(self.lib.rtx_focus_moments(self.ctx, _code(y.dtype), N, y.ptr, inc.ptr,
+                                             None if w is None else w.ptr, ptr(c), ptr(m)))
+            return red(m)
+        m = mom(None)
+        if m[0] == 0:
+            return float("nan")
+        m = mom(m[2:6]/m[0])
+        return float(-m[6]/m[7])
+
+
 _default = {}
 
 

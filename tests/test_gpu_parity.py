@@ -342,3 +342,53 @@ def test_trace_gather_epilogue(eng, systems, n):
         b.free()
     d_y0.free()
     d_u0.free()
+
+
+def test_device_refocus_shift(eng):
+    """Engine.refocus_shift == the shift GeometricTrace.refocus computes
+    (geometric_trace.py:82-99) on host arrays"""
+    c = load_golden("double_gauss_l0_clip")
+    at = -2
+    y, i, w = c["Y"][at], c["I"][at], c["w"]
+    u = i[:, :2]/i[:, 2:]
+    good = np.all(np.isfinite(u), axis=1)
+    yg, ug, wg = y[good, :2], u[good], w[good]
+    yg = yg - yg.mean(0)
+    ug = ug - ug.mean(0)
+    want = -np.dot((wg[:, None]*yg).ravel(), ug.ravel())/np.dot((wg[:, None]*ug).ravel(), ug.ravel())
+    got = eng.refocus_shift(eng.to_device(y), eng.to_device(i), eng.to_device(w))
+    assert abs(got - want) <= 1e-11*abs(want)
+
+
+def test_limits_and_degenerate_sizes(eng):
+    """N = 1, S = 1, the maximum table (S = 256) and the argument errors"""
+    from rayopt_b200._lib import RtxError
+    c = load_golden("cooke_single_ray")
+    got = eng.trace(c["table"], c["y0"], c["u0"], exact=True)
+    for a, b in zip(got, (c["Y"], c["U"], c["I"], c["T"])):
+        assert np.array_equal(a, b, equal_nan=True)
+    one = eng.trace(c["table"][:1], c["y0"], c["u0"], exact=True)
+    assert np.array_equal(one[0][0], c["Y"][0])
+    # 256 surfaces: a stack of thin plane-parallel plates (alternating n)
+    big = np.zeros(256, c["table"].dtype)
+    big["rot"] = np.eye(3).reshape(9)
+    big["offset"][:, 2] = .01
+    big["radius2"] = np.inf
+    big["n_asph"] = -1
+    nn = np.where(np.arange(256) % 2 == 0, 1.5, 1.0)
+    n0 = np.r_[1.0, nn[:-1]]
+    big["n0"], big["n"] = n0, nn
+    big["mu"] = n0/nn
+    big["muf"], big["sgn"], big["mu2m1"] = np.abs(big["mu"]), np.sign(big["mu"]), big["mu"]**2 - 1
+    rng = np.random.default_rng(0)
+    y0 = np.c_[rng.normal(0, 1, (5000, 2)), np.zeros(5000)]
+    u0 = rng.normal(0, .1, (5000, 2))
+    u0 = np.c_[u0, np.sqrt(1 - np.square(u0).sum(1))]
+    want = np_oracle.trace(big, y0, u0)
+    got = eng.trace(big, y0, u0, exact=True)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b, equal_nan=True)
+    with pytest.raises(RtxError):
+        eng.trace(np.concatenate([big, big[:1]]), y0, u0)          # 257 surfaces
+    with pytest.raises(ValueError):
+        eng.trace(big, y0[:, :2], u0[:, :2])                       # not (N, 3)
