@@ -67,6 +67,7 @@ struct rtx_ctx {
     int lockstep = 1;         // CTA barrier per stored surface (STORE_WARP)
     int max_ctas_per_sm = 0;  // 0: whatever fits
     bool tuned = false;       // an RTX_* environment knob overrides the heuristics
+    int tune = 1;             // TraceParams::tune bits (RTX_TUNE); 1 = L2 evict_first stores
 };
 
 namespace {
@@ -280,17 +281,23 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
     if (flags & RTX_RPT2) rpt = 2;
     int store = ctx->store, warps = ctx->warps, nbuf = ctx->nbuf;
     if (!ctx->tuned) {
-        // measured best configurations (profiles/r1_sweep5_configs.txt):
-        //  FP64: 16 warps x 2 rays, per-CTA bulk stores (24 KB runs)
-        //  FP32: 32 warps x 2 rays (24 KB runs again)
-        //  FP64 with Newton (aspheric) surfaces is FP64-pipe bound: 1 ray per
-        //  thread and two 16-warp CTAs per SM hide the long dependent chains
-        if (sizeof(T) == 4) {
+        // measured best configurations (profiles/r1_sweep8_defaults.txt):
+        //  FP64: 16 warps x 2 rays, per-CTA bulk stores (24 KB runs)      0.94
+        //  FP32: 32 warps x 2 rays (24 KB runs again)                     0.90
+        //  systems with >= 25 % Newton (aspheric) surfaces are bound by the
+        //  FP64/FP32 pipes and divergent iteration counts, not by HBM: small
+        //  8-warp CTAs with per-warp stores (more independent CTAs per SM),
+        //  1 ray per thread in FP64 (64 registers), 2 in FP32
+        int newton = 0;
+        for (int i = 0; i < S; ++i) newton += surf && surf[i].n_asph >= 0;
+        const bool heavy = newton * 4 >= S;
+        if (heavy && !(flags & (RTX_RPT1 | RTX_RPT2))) {
+            rpt = sizeof(T) == 4 ? 2 : 1;
+            store = STORE_WARP;
+            warps = 8;
+            nbuf = 2;
+        } else if (sizeof(T) == 4) {
             warps = 32;
-        } else {
-            int newton = 0;
-            for (int i = 0; i < S; ++i) newton += surf && surf[i].n_asph >= 0;
-            if (rpt == ctx->default_rpt && newton * 4 >= S) rpt = 1;
         }
     }
     if (N <= 32 * 1024) {  // small bundles: spread over more warps
@@ -307,6 +314,7 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
                          al16(U) && al16(I) && al16(Tt) && peers_ok;
     if (!bulk_ok) store = STORE_DIRECT;
     p.lockstep = ctx->lockstep;
+    p.tune = ctx->tune;
     return launch_trace<T>(ctx, p, (flags & RTX_EXACT) != 0, rpt, store, warps, nbuf, stream);
 }
 
@@ -511,6 +519,7 @@ int rtx_init(int device, rtx_ctx** out) {
     if (getenv("RTX_WARPS") || getenv("RTX_STORE") || getenv("RTX_NBUF")) ctx->tuned = true;
     if (const char* e = getenv("RTX_LOCK")) ctx->lockstep = atoi(e) != 0;
     if (const char* e = getenv("RTX_MAX_CTAS")) ctx->max_ctas_per_sm = atoi(e);
+    if (const char* e = getenv("RTX_TUNE")) ctx->tune = atoi(e);
     *out = ctx;
     return 0;
 }

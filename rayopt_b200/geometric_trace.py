@@ -144,52 +144,51 @@ class GeometricTrace(PropagateMixin):
         self.alias_incidence = alias_incidence
 
     def rays_given(self, y, u, l=None, w=None, ref=0):
-        """rayopt/geometric_trace.py:49-70"""
-        y, u = np.atleast_2d(y, u)
-        y, u = np.broadcast_arrays(y, u)
-        n, m = y.shape
-        if not hasattr(self, "y") or self.y.shape[1] != n:
-            self.allocate(n)
-        if l is None:
-            l = self.system.wavelengths[0]
-        if w is None:
-            w = np.ones(n)/n
-        self.w = w
+        """Load launch rays into row 0 (semantics of rayopt/geometric_trace.py:
+        49-70): `y`, `u` broadcast against each other, (N, 2) input is padded
+        with z = 0 and a forward u_z = +sqrt(1 - u_x^2 - u_y^2); the incidence
+        of row 0 is the launch direction; default weights 1/N."""
+        pos, dirn = np.broadcast_arrays(*np.atleast_2d(y, u))
+        count, width = pos.shape
+        if getattr(self, "y", None) is None or self.y.shape[1] != count:
+            self.allocate(count)
+        self.l = self.system.wavelengths[0] if l is None else l
+        self.w = np.full(count, 1./count) if w is None else w
         self.ref = ref
-        self.l = l
-        self.y[0, :, :m] = y
-        self.y[0, :, m:] = 0
-        self.u[0, :, :m] = u
-        if m < 3:  # assumes forward rays
-            u2 = np.square(self.u[0, :, :2]).sum(-1)
-            self.u[0, :, 2] = np.sqrt(1 - u2)
-        self.i[0] = self.u[0]
-        self.n[0] = self.system.refractive_index(l, 0)
+        y0, u0 = self.y[0], self.u[0]
+        y0[:, :width] = pos
+        y0[:, width:] = 0
+        u0[:, :width] = dirn
+        if width == 2:
+            u0[:, 2] = np.sqrt(1 - (u0[:, 0]**2 + u0[:, 1]**2))
+        self.i[0] = u0
         self.t[0] = 0
+        self.n[0] = self.system.refractive_index(self.l, 0)
 
     def rms(self, i=-1, ref=None):
-        """rayopt/geometric_trace.py:171-183 (not NaN-masked, like the reference)"""
-        y = self.y[i, :, :2]
-        y0 = y.mean(0) if ref is None else y[ref]
-        r = np.square(y - y0).sum(1)
-        w = self.w if self.w is not None else np.ones_like(r)/r.shape[0]
-        return np.sqrt((r*w).sum())
+        """Weighted rms spot radius at surface `i` about the mean intercept or
+        about ray `ref` (rayopt/geometric_trace.py:171-183).  Like the
+        reference it does NOT mask NaN rays."""
+        spot = self.y[i, :, :2]
+        centre = spot.mean(0) if ref is None else spot[ref]
+        d2 = ((spot - centre)**2).sum(1)
+        weights = np.full(d2.shape, 1./d2.size) if self.w is None else self.w
+        return float(np.sqrt(np.dot(d2, weights)))
 
     def refocus(self, at=-1):
-        """rayopt/geometric_trace.py:82-99"""
-        y = self.y[at, :, :2]
-        i = self.i[at]
-        u = i[:, :2]/i[:, 2:]                   # tanarcsin, utils.py:42-48
-        good = np.all(np.isfinite(u), axis=1)
-        y, u = y[good], u[good]
-        w = self.w[good] if self.w is not None else np.ones(y.shape[0])
-        y = y - y.mean(0)
-        u = u - u.mean(0)
-        wy = (w[:, None]*y).ravel()
-        wu = (w[:, None]*u).ravel()
-        u = u.ravel()
-        t = -np.dot(wy, u)/np.dot(wu, u)
-        self.system[at].distance += t
+        """Least-squares focus shift of element `at` and re-trace
+        (rayopt/geometric_trace.py:82-99): minimise sum w |y + t u|^2 about the
+        means, u = tan of the incidence angles, over the rays that arrive."""
+        inc = self.i[at]
+        slope = inc[:, :2]/inc[:, 2:]                # tanarcsin, utils.py:42-48
+        ok = np.isfinite(slope).all(1)
+        yy = self.y[at, ok, :2]
+        uu = slope[ok]
+        ww = np.ones(len(yy)) if self.w is None else self.w[ok]
+        yy = yy - yy.mean(0)
+        uu = uu - uu.mean(0)
+        shift = -(ww[:, None]*yy*uu).sum()/(ww[:, None]*uu*uu).sum()
+        self.system[at].distance += shift
         self.propagate()
 
 

@@ -8,4 +8,5 @@ timeout 900 python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_$
 timeout 900 python bench.py --exact 1 --no-e2e --no-cpu > gpurun_out/bench_${TAG}_exact.json 2>&1; tail -1 gpurun_out/bench_${TAG}_exact.json | cut -c1-250
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_${TAG}_reference.json 2>&1; tail -1 gpurun_out/bench_${TAG}_reference.json | cut -c1-300
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:trace_kernel -s 3 -c 3 --csv --log-file gpurun_out/${TAG}_dram_bytes_full_size.csv python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_dram.log 2>&1; echo "ncu dram rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 3 -c 1 -o gpurun_out/${TAG}_prof python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --rays 4000000 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"

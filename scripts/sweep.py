@@ -32,7 +32,10 @@ Y, U, I = (mem.empty((S, ld, 3), dt) for _ in range(3))
 T = mem.empty((S, ld), dt)
 alg = N*(6*w + 10*w*S)
 for cfg in a.cfgs:
-    rpt, store, warps, nbuf, lock, maxc = (int(x) for x in cfg.split(","))
+    parts = [int(x) for x in cfg.split(",")]
+    rpt, store, warps, nbuf, lock, maxc = parts[:6]
+    tune = parts[6] if len(parts) > 6 else 0
+    os.environ["RTX_TUNE"] = str(tune)
     os.environ.update(RTX_RPT=str(rpt), RTX_STORE=str(store), RTX_WARPS=str(warps),
                       RTX_NBUF=str(nbuf), RTX_LOCK=str(lock), RTX_MAX_CTAS=str(maxc))
     e = Engine(0)
@@ -49,6 +52,6 @@ for cfg in a.cfgs:
         if i >= 4:
             ms.append(t)
     m = statistics.median(ms)
-    print("rpt %d store %d warps %2d nbuf %d lock %d maxctas %d exact %d %s %s: %7.3f ms (min %.3f)  %7.1f GB/s  %.3e ray-surf/s  frac %.3f" % (
-        rpt, store, warps, nbuf, lock, maxc, a.exact, a.dtype, a.system, m, min(ms), alg/m/1e6, N*S/m*1e3, alg/m/1e6/6573.2), flush=True)
+    print("tune %d rpt %d store %d warps %2d nbuf %d lock %d maxctas %d exact %d %s %s: %7.3f ms (min %.3f)  %7.1f GB/s  %.3e ray-surf/s  frac %.3f" % (
+        tune, rpt, store, warps, nbuf, lock, maxc, a.exact, a.dtype, a.system, m, min(ms), alg/m/1e6, N*S/m*1e3, alg/m/1e6/6573.2), flush=True)
     e.close()

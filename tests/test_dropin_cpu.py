@@ -158,3 +158,39 @@ def test_element_level_entry_points_match_reference():
         ys = want[0]
         np.testing.assert_allclose(el.refract(s, ys, u0, mu, engine=eng), s.refract(ys, u0, mu),
                                    rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+def test_standalone_refocus_and_rms_match_reference():
+    """the standalone class's own rays_given / rms / refocus (written against
+    geometric_trace.py:49-99, 171-183) against the reference's"""
+    warnings.simplefilter("ignore")
+    R = ref_shim.load()
+
+    def system():
+        s = R.System(**yaml.safe_load(systems_yaml.DOUBLE_GAUSS))
+        s.update()
+        s.paraxial.refocus()
+        s[-1].distance += .3          # defocus so that refocus has work to do
+        return s
+    s1, s2 = system(), system()
+    ref = R.GeometricTrace(s1)
+    ref.rays_point((0, .7), nrays=200, distribution="hexapolar", clip=True, filter=False)
+    got = GeometricTrace(s2, engine=OracleEngine())
+    got.rays_given(ref.y[0, :, :2] if False else ref.y[0], ref.u[0], ref.l, ref.w, ref.ref)
+    got.propagate(clip=True)
+    assert np.array_equal(got.y, ref.y, equal_nan=True)
+    sub = np.isfinite(ref.y[-1, :, 0])
+    d0 = s1[-1].distance
+    ref.refocus()
+    got.refocus()
+    assert abs((s1[-1].distance - d0) - (s2[-1].distance - d0)) < 1e-12
+    np.testing.assert_allclose(got.y[-1][sub], ref.y[-1][sub], rtol=0, atol=1e-11)
+    # rms over the surviving rays (the reference's rms is not NaN-masked)
+    g2 = GeometricTrace(s2, engine=OracleEngine())
+    g2.rays_given(ref.y[0][sub], ref.u[0][sub], ref.l)
+    g2.propagate()
+    r2 = R.GeometricTrace(s2)
+    r2.rays_given(ref.y[0][sub], ref.u[0][sub], ref.l)
+    r2.propagate()
+    assert abs(g2.rms() - r2.rms()) < 1e-14 and abs(g2.rms(ref=0) - r2.rms(ref=0)) < 1e-14
