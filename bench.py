@@ -266,6 +266,11 @@ def main():
             per_launch.append(eng.last_kernel_ms())
     k_ms = statistics.mean(per_launch)
     alg_bytes = N*(6*w + 10*w*S)
+    # DRAM traffic per launch: dram__bytes_read.sum + dram__bytes_write.sum of
+    # this kernel at this size from ncu (profiles/r1_v5_dram_bytes_full_size.csv:
+    # 0.481 GB read + 9.536 GB written; the last ~64 MB of results are still
+    # in L2 when the kernel ends).  Only valid for the default workload.
+    traffic = 10_017_000_000 if (N == N_RAYS and not args.direct) else None
     achieved = alg_bytes/(k_ms*1e-3)/1e9
     peak, peak_src = peaks()
 
@@ -392,7 +397,10 @@ def main():
                        "l2": "outputs %.1f GB per launch >> 126 MB L2 (no flush needed)"
                              % (alg_bytes/1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved/peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved/peak, "traffic": traffic,
+                         "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum per launch, "
+                                           "profiles/r1_v5_dram_bytes_full_size.csv",
+                         "peak_source": peak_src,
                          "kernel": "rtx::trace_kernel<double>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,

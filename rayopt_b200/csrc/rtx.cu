@@ -391,8 +391,14 @@ int trace_host(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0,
     const DevSurf<T>* table = nullptr;
     int rc = upload_table<T>(ctx, surf, S, ctx->stream, &table);
     if (rc) return rc;
-    cudaEvent_t table_ready;
-    CK(cudaEventCreateWithFlags(&table_ready, cudaEventDisableTiming));
+    struct EventGuard {  // destroyed on every return path
+        cudaEvent_t e = nullptr;
+        ~EventGuard() {
+            if (e) cudaEventDestroy(e);
+        }
+    } guard;
+    CK(cudaEventCreateWithFlags(&guard.e, cudaEventDisableTiming));
+    cudaEvent_t table_ready = guard.e;
     CK(cudaEventRecord(table_ready, ctx->stream));
     clear_chunk_events(ctx);
     int nchunk = 0;
@@ -404,15 +410,21 @@ int trace_host(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0,
                            cudaMemcpyHostToDevice, cb.stream));
         CK(cudaMemcpyAsync(cb.u0, (const T*)u0 + c0 * 3, (size_t)n * 3 * sizeof(T),
                            cudaMemcpyHostToDevice, cb.stream));
-        cudaEvent_t e0, e1;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
         CK(cudaEventCreate(&e0));
-        CK(cudaEventCreate(&e1));
-        ctx->chunk_events.emplace_back(e0, e1);
+        if (cudaError_t er = cudaEventCreate(&e1)) {
+            cudaEventDestroy(e0);
+            return (int)er;
+        }
+        ctx->chunk_events.emplace_back(e0, e1);  // owned by ctx from here on
         CK(cudaEventRecord(e0, cb.stream));
         rc = trace_device<T>(ctx, surf, S, rot0, n, cb.y0, cb.u0, clip, keep, C, Y ? cb.Y : nullptr,
                              U ? cb.U : nullptr, I ? cb.I : nullptr, Tt ? cb.T : nullptr, flags,
                              cb.stream, table);
-        if (rc) return rc;
+        if (rc) {
+            for (int b = 0; b < 2; ++b) cudaStreamSynchronize(ctx->chunk[b].stream);
+            return rc;
+        }
         CK(cudaEventRecord(e1, cb.stream));
         const size_t w3 = (size_t)n * 3 * sizeof(T), w1 = (size_t)n * sizeof(T);
         const size_t sp3 = (size_t)C * 3 * sizeof(T), sp1 = (size_t)C * sizeof(T);
@@ -431,7 +443,6 @@ int trace_host(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0,
                                  cb.stream));
     }
     for (int b = 0; b < 2; ++b) CK(cudaStreamSynchronize(ctx->chunk[b].stream));
-    CK(cudaEventDestroy(table_ready));
     ctx->kernel_timed = false;
     return 0;
 }
@@ -488,16 +499,23 @@ int rtx_init(int device, rtx_ctx** out) {
     rtx_ctx* ctx = new (std::nothrow) rtx_ctx();
     if (!ctx) return RTX_E_NOMEM;
     ctx->device = device;
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    ctx->sm_count = prop.multiProcessorCount;
-    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&ctx->t0));
-    CK(cudaEventCreate(&ctx->t1));
-    CK(cudaEventCreate(&ctx->k0));
-    CK(cudaEventCreate(&ctx->k1));
-    CK(cudaMalloc((void**)&ctx->d_moments, 8 * sizeof(double)));
+    auto setup = [&]() -> int {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        ctx->sm_count = prop.multiProcessorCount;
+        ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&ctx->t0));
+        CK(cudaEventCreate(&ctx->t1));
+        CK(cudaEventCreate(&ctx->k0));
+        CK(cudaEventCreate(&ctx->k1));
+        CK(cudaMalloc((void**)&ctx->d_moments, 8 * sizeof(double)));
+        return 0;
+    };
+    if (int rc = setup()) {
+        rtx_free(ctx);
+        return rc;
+    }
     // tuning knobs (experiments; the defaults above are the measured best)
     if (const char* e = getenv("RTX_RPT")) {
         int v = atoi(e);
@@ -537,11 +555,11 @@ int rtx_free(rtx_ctx* ctx) {
     free_chunk(ctx->chunk[0]);
     free_chunk(ctx->chunk[1]);
     if (ctx->d_moments) cudaFree(ctx->d_moments);
-    cudaEventDestroy(ctx->t0);
-    cudaEventDestroy(ctx->t1);
-    cudaEventDestroy(ctx->k0);
-    cudaEventDestroy(ctx->k1);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
+    if (ctx->k0) cudaEventDestroy(ctx->k0);
+    if (ctx->k1) cudaEventDestroy(ctx->k1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
 }
@@ -745,20 +763,24 @@ int rtx_trace_gather(rtx_ctx* ctx, const rtx_surface* surf, int S, const double*
 int rtx_selftest_math(rtx_ctx* ctx, int64_t n, const double* a, const double* b, double* out) {
     if (!ctx || n < 1 || !a || !b || !out) return RTX_E_BADARG;
     CK(cudaSetDevice(ctx->device));
-    double *da = nullptr, *db = nullptr, *dout = nullptr;
-    CK(cudaMalloc((void**)&da, n * sizeof(double)));
-    CK(cudaMalloc((void**)&db, n * sizeof(double)));
-    CK(cudaMalloc((void**)&dout, 6 * n * sizeof(double)));
-    CK(cudaMemcpyAsync(da, a, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(db, b, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    selftest_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(da, db, dout, n);
+    struct Bufs {  // freed on every return path
+        double *a = nullptr, *b = nullptr, *o = nullptr;
+        ~Bufs() {
+            cudaFree(a);
+            cudaFree(b);
+            cudaFree(o);
+        }
+    } d;
+    CK(cudaMalloc((void**)&d.a, n * sizeof(double)));
+    CK(cudaMalloc((void**)&d.b, n * sizeof(double)));
+    CK(cudaMalloc((void**)&d.o, 6 * n * sizeof(double)));
+    CK(cudaMemcpyAsync(d.a, a, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d.b, b, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    selftest_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d.a, d.b, d.o, n);
     ctx->launches++;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, dout, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out, d.o, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(da);
-    cudaFree(db);
-    cudaFree(dout);
     return 0;
 }
 
