@@ -57,6 +57,10 @@ struct rtx_ctx {
     size_t slot_bytes = 0;
     ChunkBuf chunk[2];
     double* d_moments = nullptr;
+    // small-bundle latency path (ray aiming: hundreds of 1-3 ray traces)
+    void* small_host = nullptr;  // pinned: [y0|u0] in, [Y|U|I|T] out
+    void* small_dev = nullptr;
+    size_t small_bytes = 0;
     int64_t launches = 0;
     int max_smem_optin = 0;
     // kernel configuration (defaults = measured best, profiles/r1_sweep*.txt)
@@ -369,11 +373,66 @@ void clear_chunk_events(rtx_ctx* ctx) {
     ctx->chunk_events.clear();
 }
 
+constexpr size_t SMALL_PATH_BYTES = 4u << 20;
+
+// Latency path for small bundles (aim_chief / aim_marginal issue hundreds of
+// 1-3 ray traces, rayopt/system.py:507-555): one pinned bounce buffer, ONE
+// H2D of [y0|u0], the kernel with ld = N (per-thread stores, reference
+// layout on the device), ONE D2H of [Y|U|I|T], one synchronisation.
+template <typename T>
+int trace_host_small(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0,
+                     long long N, const void* y0, const void* u0, int clip, int keep, void* Y,
+                     void* U, void* I, void* Tt, unsigned flags, size_t in_bytes,
+                     size_t out_bytes) {
+    const int rows = keep == RTX_KEEP_LAST ? 1 : S;
+    const size_t need = in_bytes + out_bytes;
+    if (need > ctx->small_bytes) {
+        if (ctx->small_host) CK(cudaFreeHost(ctx->small_host));
+        if (ctx->small_dev) CK(cudaFree(ctx->small_dev));
+        ctx->small_host = ctx->small_dev = nullptr;
+        ctx->small_bytes = 0;
+        size_t nb = need < (256u << 10) ? (256u << 10) : need;
+        CK(cudaMallocHost(&ctx->small_host, nb));
+        CK(cudaMalloc(&ctx->small_dev, nb));
+        ctx->small_bytes = nb;
+    }
+    char* h = (char*)ctx->small_host;
+    char* d = (char*)ctx->small_dev;
+    const size_t v3 = (size_t)N * 3 * sizeof(T), r3 = (size_t)rows * v3, r1 = r3 / 3;
+    memcpy(h, y0, v3);
+    memcpy(h + v3, u0, v3);
+    CK(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    char* dY = d + in_bytes;
+    char *dU = dY + r3, *dI = dU + r3, *dT = dI + r3;
+    int rc = trace_device<T>(ctx, surf, S, rot0, N, d, d + v3, clip, keep, N, Y ? dY : nullptr,
+                             U ? dU : nullptr, I ? dI : nullptr, Tt ? dT : nullptr,
+                             flags | RTX_STORE_DIRECT, ctx->stream, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h + in_bytes, dY, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const char* o = h + in_bytes;
+    if (Y) memcpy(Y, o, r3);
+    if (U) memcpy(U, o + r3, r3);
+    if (I) memcpy(I, o + 2 * r3, r3);
+    if (Tt) memcpy(Tt, o + 3 * r3, r1);
+    clear_chunk_events(ctx);
+    ctx->kernel_timed = false;
+    return 0;
+}
+
 template <typename T>
 int trace_host(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0, long long N,
                const void* y0, const void* u0, int clip, int keep, void* Y, void* U, void* I,
                void* Tt, unsigned flags) {
     const int rows = keep == RTX_KEEP_LAST ? 1 : S;
+    {
+        const size_t in_b = (size_t)N * 6 * sizeof(T);
+        const size_t out_b = (size_t)rows * N * 10 * sizeof(T);
+        // (an explicit store-path / RPT request goes through the general path)
+        if (in_b + out_b <= SMALL_PATH_BYTES && !(flags & (RTX_RPT1 | RTX_RPT2 | RTX_STORE_DIRECT)))
+            return trace_host_small<T>(ctx, surf, S, rot0, N, y0, u0, clip, keep, Y, U, I, Tt,
+                                       flags, in_b, out_b);
+    }
     // chunk: ~256 MB of results, whole 64-ray groups
     long long per_ray = (long long)rows * 10 * sizeof(T) + 6 * sizeof(T);
     long long C = (256ll << 20) / per_ray;
@@ -555,6 +614,8 @@ int rtx_free(rtx_ctx* ctx) {
     free_chunk(ctx->chunk[0]);
     free_chunk(ctx->chunk[1]);
     if (ctx->d_moments) cudaFree(ctx->d_moments);
+    if (ctx->small_host) cudaFreeHost(ctx->small_host);
+    if (ctx->small_dev) cudaFree(ctx->small_dev);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->k0) cudaEventDestroy(ctx->k0);
