@@ -145,7 +145,9 @@ def test_random_analytic_unrotated_bit_exact(eng, seed):
     got = eng.trace(table, y0, u0, clip=clip, exact=True)
     for a, b, w in zip(got, want, "yuit"):
         assert np.array_equal(a, b, equal_nan=True), "seed %d %s" % (seed, w)
-    ok = well_conditioned(table, y0, u0, want, clip) & reference_accurate(table, y0, u0, want, clip)
+    # (no reference_accurate() filter here: the fast mode evaluates the
+    # cancellation-prone analytic intercept with the reference's own roundings)
+    ok = well_conditioned(table, y0, u0, want, clip)
     assert ok.mean() > .5, ok.mean()
     got = eng.trace(table, y0, u0, clip=clip)
     for a, b, w in zip(masked(got, ok), masked(want, ok), "yuit"):
