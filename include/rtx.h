@@ -186,6 +186,16 @@ int rtx_trace(rtx_ctx *ctx, const rtx_surface *surf, int S,
               void *Y, void *U, void *I, void *T, unsigned flags);
 
 /*
+ * Optional warp-ballot vignetting mask for the following rtx_trace /
+ * rtx_trace_gather calls on device buffers: dmask (DEVICE, ceil(N/32) words,
+ * or NULL to switch it off) receives bit (ray % 32) of word ray / 32 = 1 when
+ * the ray leaves the last traced surface with a finite direction -- i.e. it
+ * was not clipped (Element.clip, elements.py:206-209) and hit no NaN
+ * condition on the way (elements.py:347-348, 367, 496).
+ */
+int rtx_set_mask_output(rtx_ctx *ctx, uint32_t *dmask);
+
+/*
  * Same call with HOST buffers in the reference layout: y0,u0 (N,3);
  * Y,U,I (rows,N,3), T (rows,N) C-contiguous (GeometricTrace.y/u/i/t rows
  * start..stop-1).  Rays are processed in chunks; H2D, kernel and D2H of

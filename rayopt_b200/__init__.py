@@ -11,6 +11,7 @@ from .geometric_trace import (GeometricTrace, PropagateMixin, bind,  # noqa: F40
                               system_propagate, install)
 from .engine import Engine, DeviceArray, default_engine  # noqa: F401
 from . import elements  # noqa: F401
+from .lazy import LazyRows, ResidentTrace  # noqa: F401
 from ._lib import RtxError  # noqa: F401
 
 __version__ = "0.1.0"

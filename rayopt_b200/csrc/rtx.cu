@@ -70,6 +70,7 @@ struct rtx_ctx {
     int nbuf = 1;             // staging buffers per CTA
     int lockstep = 1;         // CTA barrier per stored surface (STORE_WARP)
     int max_ctas_per_sm = 0;  // 0: whatever fits
+    unsigned* mask = nullptr; // rtx_set_mask_output
     bool tuned = false;       // an RTX_* environment knob overrides the heuristics
     int tune = 1;             // TraceParams::tune bits (RTX_TUNE); 1 = L2 evict_first stores
 };
@@ -319,6 +320,7 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
     if (!bulk_ok) store = STORE_DIRECT;
     p.lockstep = ctx->lockstep;
     p.tune = ctx->tune;
+    p.mask = ctx->mask;
     return launch_trace<T>(ctx, p, (flags & RTX_EXACT) != 0, rpt, store, warps, nbuf, stream);
 }
 
@@ -760,9 +762,20 @@ int rtx_trace_host(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* r
     if (dtype != RTX_F64 && dtype != RTX_F32) return RTX_E_BADARG;
     if (N == 0) return 0;
     CK(cudaSetDevice(ctx->device));
+    unsigned* saved = ctx->mask;  // the mask belongs to device-buffer traces
+    ctx->mask = nullptr;
     if (dtype == RTX_F64)
-        return trace_host<double>(ctx, surf, S, rot0, N, y0, u0, clip, keep, Y, U, I, T, flags);
-    return trace_host<float>(ctx, surf, S, rot0, N, y0, u0, clip, keep, Y, U, I, T, flags);
+        rc = trace_host<double>(ctx, surf, S, rot0, N, y0, u0, clip, keep, Y, U, I, T, flags);
+    else
+        rc = trace_host<float>(ctx, surf, S, rot0, N, y0, u0, clip, keep, Y, U, I, T, flags);
+    ctx->mask = saved;
+    return rc;
+}
+
+int rtx_set_mask_output(rtx_ctx* ctx, uint32_t* dmask) {
+    if (!ctx) return RTX_E_BADARG;
+    ctx->mask = dmask;
+    return 0;
 }
 
 int rtx_ipc_export(rtx_ctx* ctx, void* dptr, unsigned char* handle) {

@@ -169,16 +169,22 @@ class Engine:
                 | {0: 0, 1: RTX_RPT1, 2: RTX_RPT2}[rpt])
 
     def trace_device(self, table, y0, u0, Y, U, I, T, N=None, ld=None, clip=False,
-                     keep_last=False, rot0=None, exact=False, direct=False, rpt=0):
+                     keep_last=False, rot0=None, exact=False, direct=False, rpt=0, mask=None):
         """One launch on DEVICE arrays (DeviceArray or None for outputs).
-        Asynchronous on the engine stream."""
+        Asynchronous on the engine stream.  `mask`: optional uint32
+        DeviceArray of ceil(N/32) words receiving the warp-ballot vignetting
+        mask (bit set = the ray survives the last surface)."""
         table = self._table(table)
         dt = _code(y0.dtype)
         N = y0.shape[0] if N is None else int(N)
-        first = next(a for a in (Y, U, I, T) if a is not None)
-        ld = first.shape[1] if ld is None else int(ld)
+        first = next((a for a in (Y, U, I, T) if a is not None), None)
+        if ld is None:
+            ld = first.shape[1] if first is not None else (N + 63)//64*64
         r0 = None if rot0 is None else np.ascontiguousarray(rot0, np.float64).reshape(9)
         dp = lambda a: None if a is None else a.ptr  # noqa: E731
+        if mask is None and all(a is None for a in (Y, U, I, T)):
+            raise ValueError("nothing to store: pass an output array or a mask")
+        check(self.lib.rtx_set_mask_output(self.ctx, dp(mask)))
         check(self.lib.rtx_trace(
             self.ctx, ptr(table), len(table), ptr(r0), dt, N, y0.ptr, u0.ptr,
             int(bool(clip)), RTX_KEEP_LAST if keep_last else RTX_KEEP_ALL, ld,

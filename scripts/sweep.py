@@ -18,7 +18,7 @@ ap.add_argument("--rays", type=int, default=10_000_000)
 ap.add_argument("--exact", type=int, default=0)
 ap.add_argument("--system", default="double_gauss")
 ap.add_argument("--dtype", default="f64")
-ap.add_argument("cfgs", nargs="*", default=["2,1,8,2,1,0"])
+ap.add_argument("cfgs", nargs="*", default=["2,2,16,1,0,0,1"])
 a = ap.parse_args()
 ent = bench.load_system(a.system)
 S, N = ent["S"], a.rays

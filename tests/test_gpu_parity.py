@@ -392,3 +392,68 @@ def test_limits_and_degenerate_sizes(eng):
         eng.trace(np.concatenate([big, big[:1]]), y0, u0)          # 257 surfaces
     with pytest.raises(ValueError):
         eng.trace(big, y0[:, :2], u0[:, :2])                       # not (N, 3)
+
+
+@pytest.mark.parametrize("n", [1000, 70001])
+def test_vignetting_mask_ballot(eng, systems, n):
+    """rtx_set_mask_output: the warp-ballot mask equals isfinite(u[-1]) of the
+    reference trace, also when nothing else is stored"""
+    ent = systems["double_gauss"]
+    table, aim = ent["tables"][2], ent["aim"][2][5]          # full field: ~7 % vignetted
+    y0, u0 = aim_infinite(aim["field"], disc(n, 3), aim["z"], aim["p"], ent["object_angle"])
+    want = np.isfinite(np_oracle.trace(table, y0, u0, clip=True)[1][-1, :, 0])
+    assert 0 < want.mean() < 1
+    d_y0, d_u0 = eng.to_device(y0), eng.to_device(u0)
+    mask = eng.empty(((n + 31)//32,), np.uint32)
+    for keep in ("last", "none"):
+        eng.lib.rtx_memset(eng.ctx, mask.ptr, 0, mask.nbytes)
+        Y = eng.empty((1, (n + 63)//64*64, 3)) if keep == "last" else None
+        eng.trace_device(table, d_y0, d_u0, Y, None, None, None, N=n, clip=True, keep_last=True,
+                         mask=mask)
+        eng.sync()
+        bits = np.unpackbits(mask.download().view(np.uint8), bitorder="little")[:n].astype(bool)
+        assert np.array_equal(bits, want)
+    check_off = eng.empty((2, 64, 3))
+    eng.trace_device(table[:2], eng.to_device(y0[:10]), eng.to_device(u0[:10]), check_off, None,
+                     None, None, N=10, clip=True)            # mask switched off again
+    eng.sync()
+
+
+def test_resident_trace_lazy_rows(eng, systems):
+    """ResidentTrace: results stay in HBM, rows come to the host on demand,
+    sub-range propagate starts from the resident row, rms never moves rays"""
+    from rayopt_b200 import PackedSystem, ResidentTrace
+    ent = systems["double_gauss"]
+    ps = PackedSystem(ent["wavelengths"], ent["tables"], [n[0] for n in ent["n"]])
+    c = load_golden("double_gauss_l0_clip")
+    g = ResidentTrace(ps, engine=eng, exact=True)
+    g.rays_given(c["y0"], c["u0"], l=ent["wavelengths"][0], w=c["w"])
+    g.propagate(clip=True)
+    assert g.y.fetched_bytes == 0                     # nothing copied yet
+    assert np.array_equal(g.y[-1], c["Y"][-1], equal_nan=True)
+    assert np.array_equal(g.y[-1, :, :2], c["Y"][-1, :, :2], equal_nan=True)
+    assert np.array_equal(g.i[-1], c["I"][-1], equal_nan=True)
+    assert g.y.fetched_bytes == g._ld*24 and g.u.fetched_bytes == 0
+    assert np.array_equal(g.y[0], c["y0"]) and np.array_equal(g.u[0], c["u0"])
+    assert np.array_equal(np.asarray(g.t)[1:], c["T"], equal_nan=True)
+    assert np.array_equal(g.u[3:5], c["U"][2:4], equal_nan=True)
+    assert np.array_equal(g.n[1:], c["n"])
+    # sub-range re-trace from a resident row (geometric_trace.py:72-80)
+    c2 = load_golden("double_gauss_sub_4_9")
+    g2 = ResidentTrace(ps, engine=eng, exact=True)
+    g2.rays_given(c2["y0"], c2["u0"], l=ent["wavelengths"][0])   # any rays: rows are overwritten
+    g2.y.set_row(3, np.pad(c2["y0"], ((0, g2._ld - len(c2["y0"])), (0, 0))))
+    g2.u.set_row(3, np.pad(c2["u0"], ((0, g2._ld - len(c2["u0"])), (0, 0))))
+    g2.n[3] = c2["table"]["n0"][0]
+    g2.propagate(start=4, stop=9, clip=True)
+    assert np.array_equal(g2.y[4:9], c2["Y"], equal_nan=True)
+    assert np.array_equal(g2.t[4:9], c2["T"], equal_nan=True)
+    # device rms == reference rms on the surviving rays
+    k = load_golden("cooke_radau13")
+    pk = PackedSystem([587.56e-9], [k["table"]], [k["table"]["n0"][0]])
+    gk = ResidentTrace(pk, engine=eng, exact=True)
+    gk.rays_given(k["y0"], k["u0"], l=587.56e-9, w=k["w"])
+    gk.propagate()
+    assert abs(gk.rms() - k["meta"]["rms"]) < 1e-13 and gk.y.fetched_bytes == 0
+    for t in (g, g2, gk):
+        t.free()
