@@ -353,6 +353,35 @@ def main():
                             "d2h_bytes_per_step": nl*N*S*10*w,
                             "api": "rtx_trace_host with y,u,i,t host outputs"}
 
+    # ---- e2e for a spot-diagram consumer (rayopt/analysis.py:269-280): the
+    # trace stays in HBM (rayopt_b200.ResidentTrace semantics), per wavelength
+    # the launch rays go up and only y[-1] comes back
+    if not args.no_e2e and world == 1:
+        from rayopt_b200._lib import check, ptr
+        d_in = (eng.empty((N, 3)), eng.empty((N, 3)))
+        d_full = {"Y": eng.empty((S, ld, 3)), "U": eng.empty((S, ld, 3)),
+                  "I": eng.empty((S, ld, 3)), "T": eng.empty((S, ld))}
+        h_spot = eng.pinned_empty((N, 3))
+
+        def spot_step():
+            for li in range(nl):
+                check(eng.lib.rtx_memcpy_h2d(eng.ctx, d_in[0].ptr, ptr(pin[li][0]), pin[li][0].nbytes))
+                check(eng.lib.rtx_memcpy_h2d(eng.ctx, d_in[1].ptr, ptr(pin[li][1]), pin[li][1].nbytes))
+                eng.trace_device(ent["tables"][li], d_in[0], d_in[1], d_full["Y"], d_full["U"],
+                                 d_full["I"], d_full["T"], N=N, ld=ld, clip=True,
+                                 exact=bool(args.exact))
+                check(eng.lib.rtx_memcpy_d2h(eng.ctx, ptr(h_spot), d_full["Y"].rows(S - 1).ptr,
+                                             h_spot.nbytes))
+            eng.sync()
+        ssteps = max(1, min(args.steps, 5))
+        dt = timed(spot_step, ssteps)
+        e2e["spot_consumer"] = {"value": nl*N*S*ssteps/dt, "ms_per_step": dt/ssteps*1e3,
+                                "h2d_bytes_per_step": nl*N*6*w, "d2h_bytes_per_step": nl*N*3*w,
+                                "api": "device-resident full trace (ResidentTrace semantics): rays "
+                                       "up, kernel, only y[-1] back"}
+        for a in list(d_in) + list(d_full.values()):
+            a.free()
+
     # ---- CPU baseline: numpy port of the reference path ------------------
     # (also the checker of the timed GPU results: same rays, same tables)
     cpu = None
