@@ -194,3 +194,59 @@ def test_standalone_refocus_and_rms_match_reference():
     r2.rays_given(ref.y[0][sub], ref.u[0][sub], ref.l)
     r2.propagate()
     assert abs(g2.rms() - r2.rms()) < 1e-14 and abs(g2.rms(ref=0) - r2.rms(ref=0)) < 1e-14
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+def test_reference_own_raytrace_tests_through_the_dropin():
+    """The reference's own integration tests for this path
+    (rayopt/test/test_raytrace.py:151-199: test_aim_point, test_aim_point_more,
+    test_quadrature) re-run with BOTH call sites replaced -- System.propagate
+    (ray aiming) and GeometricTrace.allocate/propagate -- i.e. as the API
+    conformance suite of the drop-in (engine: the oracle stand-in on CPU)."""
+    warnings.simplefilter("ignore")
+    R = ref_shim.load()
+    import rayopt_b200
+
+    class System(R.System):          # patched copies: leave the shared classes alone
+        pass
+
+    class Trace(R.GeometricTrace):
+        pass
+    rayopt_b200.install(System, Trace, engine=OracleEngine())
+    s = System(**yaml.safe_load(systems_yaml.COOKE))
+    s.update()
+    s.paraxial.refocus()
+    s.paraxial.update_conjugates()
+    calls0 = OracleEngine.calls
+    g = Trace(s)
+    # test_aim_point
+    g.rays_point((0, 1.))
+    g.rays_clipping((0, 1.))
+    g.rays_line((0, 1.))
+    # test_aim_point_more
+    i = s.stop
+    r = np.array([el.radius for el in s[1:-1]])
+    g.rays_clipping((0, 1.))
+    np.testing.assert_allclose(g.u[0, :, :], g.u[0, (0,)*g.u.shape[1], :])
+    np.testing.assert_allclose(g.y[i, 0, 1], 0, atol=5e-3)
+    np.testing.assert_allclose(min(g.y[1:-1, 1, 1] + r), 0, atol=1e-3)
+    np.testing.assert_allclose(max(g.y[1:-1, 2, 1] - r), 0, atol=1e-3)
+    g.rays_point((0, 1.), distribution="cross", nrays=5, filter=False)
+    np.testing.assert_allclose(g.y[i, :3, 1]/s[i].radius, [-1, 0, 1], atol=1e-3, rtol=3e-2)
+    np.testing.assert_allclose(g.y[i, :, 0]/s[i].radius, [0, 0, 0, -1, 0, 1], atol=1e-1)
+    # test_quadrature: the known answer of the path
+    g.rays_point((0, 1.), nrays=13, distribution="radau", filter=False)
+    a = g.rms()
+    np.testing.assert_allclose(a, .052, rtol=1e-2)
+    g.rays_point((0, 1.), nrays=500, distribution="square", clip=False, filter=True)
+    np.testing.assert_allclose(a, g.rms(), rtol=5e-2)
+    assert OracleEngine.calls - calls0 > 50          # aiming really went through the engine
+    # and the aim solution equals the unpatched reference's
+    s0 = R.System(**yaml.safe_load(systems_yaml.COOKE))
+    s0.update()
+    s0.paraxial.refocus()
+    s0.paraxial.update_conjugates()
+    z0, p0 = s0.pupil((0, 1.))
+    z1, p1 = s.pupil((0, 1.))
+    np.testing.assert_allclose(z1, z0, rtol=1e-12)
+    np.testing.assert_allclose(p1, p0, rtol=1e-12)

@@ -194,6 +194,9 @@ def test_known_answer_rms_through_dropin(eng):
     rms = np_oracle.rms(Y[-1], c["w"])
     assert abs(rms - 0.052)/0.052 < 1e-2
     assert rms == c["meta"]["rms"]
+    q = load_golden("cooke_square500")                 # test_raytrace.py:196-199
+    Yq = eng.trace(q["table"], q["y0"], q["u0"])[0]
+    assert abs(np_oracle.rms(Yq[-1], q["w"]) - rms)/rms < 5e-2
 
 
 def test_moments_and_device_rms(eng):

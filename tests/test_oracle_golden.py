@@ -36,6 +36,10 @@ def test_known_answer_rms():
     rms = np_oracle.rms(Y[-1], c["w"], ref=None)
     assert abs(rms - 0.052)/0.052 < 1e-2
     assert abs(rms - c["meta"]["rms"]) < 1e-15
+    # ...and the 500-ray square grid agrees with it to 5 % (test_raytrace.py:196-199)
+    q = load_golden("cooke_square500")
+    Yq = np_oracle.trace(q["table"], q["y0"], q["u0"], clip=False)[0]
+    assert abs(np_oracle.rms(Yq[-1], q["w"]) - rms)/rms < 5e-2
 
 
 def test_golden_covers_edge_cases():
