@@ -260,6 +260,22 @@ int rtx_selftest_math(rtx_ctx *ctx, int64_t n, const double *a, const double *b,
 int rtx_moments(rtx_ctx *ctx, int dtype, int64_t N, const void *y,
                 const void *w, const double *center, double *m);
 
+/* ---- launch rays generated in HBM -------------------------- */
+/*
+ * Aimed bundle for an infinite conjugate (InfiniteConjugate.aim, rectilinear
+ * projection, rayopt/conjugates.py:208-213,236-255; plane object surface) for
+ * ONE field point: frame = {u[3], ybase[3], s[3], m[3]} (host, 12 doubles: the
+ * common direction, yz - z*u, and the normalised sagittal / meridional
+ * vectors of rayopt/utils.py:102-114), pmax = fabs(p).max() (Pupil.map,
+ * rayopt/pupils.py:100).  Pupil coordinates: yp DEVICE (N,2) of `dtype`, or
+ * NULL for the hexapolar grid of pupil_distribution (rayopt/utils.py:174-180)
+ * with `hex_rings` rings, N = 1 + 3*hex_rings*(hex_rings+1).  Writes DEVICE
+ * y0,u0 (N,3).  Asynchronous on the context stream.
+ */
+int rtx_aim_infinite(rtx_ctx *ctx, int dtype, int64_t N, const void *yp,
+                     int hex_rings, const double *frame, double pmax, void *y0,
+                     void *u0);
+
 /*
  * Moments for GeometricTrace.refocus (rayopt/geometric_trace.py:82-99) on
  * DEVICE arrays of one surface: y = intercepts (N,3), inc = incidence

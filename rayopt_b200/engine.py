@@ -255,6 +255,23 @@ class Engine:
     def ipc_close(self, p):
         check(self.lib.rtx_ipc_close(self.ctx, p))
 
+    def aim_infinite_device(self, yo, z, p, angle, yp=None, nrays=None, dtype=np.float64):
+        """Launch rays of an aimed bundle generated in HBM (rtx_aim_infinite):
+        `yp` a DEVICE (N,2) array of pupil coordinates, or None for the
+        hexapolar grid with about `nrays` rays.  Returns DeviceArrays (y0, u0)."""
+        from .rays import aim_frame
+        frame = np.ascontiguousarray(np.concatenate(aim_frame(yo, z, angle)), np.float64)
+        pmax = float(np.fabs(np.asarray(p, float)).max())
+        if yp is None:
+            rings = int(np.sqrt(nrays/3. - 1/12.) - 1/2.)
+            N = 1 + 3*rings*(rings + 1)
+        else:
+            rings, N = 0, yp.shape[0]
+        y0, u0 = self.empty((N, 3), dtype), self.empty((N, 3), dtype)
+        check(self.lib.rtx_aim_infinite(self.ctx, _code(dtype), N, None if yp is None else yp.ptr,
+                                        rings, ptr(frame), pmax, y0.ptr, u0.ptr))
+        return y0, u0
+
     def selftest_math(self, a, b):
         """(6, n): engine a/b, IEEE a/b, engine sqrt(a), IEEE sqrt(a),
         engine 1/sqrt(a), IEEE 1/sqrt(a)"""

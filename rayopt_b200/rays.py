@@ -19,6 +19,36 @@ def disc(n, seed):
     return np.c_[r*np.cos(phi), r*np.sin(phi)]
 
 
+def hexapolar(nrays):
+    """pupil_distribution("hexapolar", nrays) (rayopt/utils.py:174-180):
+    returns (rings, xy (N,2)); N = 1 + 3 rings (rings + 1)"""
+    n = int(np.sqrt(nrays/3. - 1/12.) - 1/2.)
+    l = [np.zeros((2, 1))]
+    for i in range(1, n + 1):
+        a = np.linspace(0, 2*np.pi, 6*i, endpoint=False)
+        l.append([np.sin(a)*i/n, np.cos(a)*i/n])
+    return n, np.concatenate(l, axis=1).T
+
+
+def aim_frame(yo, z, angle):
+    """The per-field constants of aim_infinite: (u, ybase, s, m), each (3,):
+    the common ray direction, yz - z*u, and the normalised sagittal and
+    meridional pupil axes."""
+    yo = np.atleast_2d(np.asarray(yo, float))
+    yt = yo*np.tan(angle)
+    u = np.hstack((yt, np.ones((1, 1))))
+    u /= np.sqrt(np.square(u).sum(-1))[:, None]
+    yz = np.array((0, 0, z), float)
+    ybase = yz - z*u
+    s = np.cross(u, yz)
+    if np.all(s == 0):
+        s = np.array([[1., 0, 0]])
+    m = np.cross(u, s)
+    s = s/np.sqrt(np.square(s).sum(-1))[..., None]
+    m = m/np.sqrt(np.square(m).sum(-1))[..., None]
+    return u[0], ybase[0], s[0], m[0]
+
+
 def aim_infinite(yo, yp, z, p, angle):
     """Rays (y, u), each (N, 3), for fractional object coordinate `yo` (2,),
     fractional pupil coordinates `yp` (N, 2), pupil distance `z`, pupil
