@@ -133,6 +133,36 @@ class ResidentTrace:
         self.t.invalidate()
         self.n[0] = self.system.refractive_index(self.l, 0)
 
+    def rays_infinite(self, yo, z, p, angle, l=None, nrays=None, yp=None, ref=0):
+        """Launch rays of an aimed bundle for an infinite conjugate generated
+        directly in HBM (Engine.aim_infinite_device / rtx_aim_infinite): the
+        hexapolar grid with about `nrays` rays, or the DEVICE pupil coordinates
+        `yp` (N,2); (z, p) is the reference's pupil-aiming solution
+        (System.pupil).  Nothing crosses PCIe."""
+        from ._lib import check, ptr
+        from .rays import aim_frame
+        eng = self.engine
+        if yp is None:
+            rings = int(np.sqrt(nrays/3. - 1/12.) - 1/2.)
+            count = 1 + 3*rings*(rings + 1)
+        else:
+            rings, count = 0, yp.shape[0]
+        if self._dev is None or self.nrays != count:
+            self.allocate(count)
+        self.l = self.system.wavelengths[0] if l is None else l
+        self.w = np.full(count, 1./count)
+        self.ref = ref
+        frame = np.ascontiguousarray(np.concatenate(aim_frame(yo, z, angle)), np.float64)
+        pmax = float(np.fabs(np.asarray(p, float)).max())
+        for dst in ("u", "i"):           # i[0] = u[0] (geometric_trace.py:68)
+            check(eng.lib.rtx_aim_infinite(eng.ctx, 0, count, None if yp is None else yp.ptr,
+                                           rings, ptr(frame), pmax, self._dev["y"].rows(0).ptr,
+                                           self._dev[dst].rows(0).ptr))
+        self._dev["t"].rows(0).upload(np.zeros(self._ld))
+        for a in (self.y, self.u, self.i, self.t):
+            a.invalidate()
+        self.n[0] = self.system.refractive_index(self.l, 0)
+
     def propagate(self, start=1, stop=None, clip=False):
         init = start - 1
         table, n, rot0 = pack_system(self.system, self.l, start, stop, n0=self.n[init])

@@ -458,7 +458,18 @@ def test_resident_trace_lazy_rows(eng, systems):
     gk.rays_given(k["y0"], k["u0"], l=587.56e-9, w=k["w"])
     gk.propagate()
     assert abs(gk.rms() - k["meta"]["rms"]) < 1e-13 and gk.y.fetched_bytes == 0
-    for t in (g, g2, gk):
+    # launch rays generated in HBM: same trace as from host rays
+    aim = ent["aim"][0][3]
+    gd = ResidentTrace(ps, engine=eng, exact=True)
+    gd.rays_infinite(aim["field"], aim["z"], aim["p"], ent["object_angle"],
+                     l=ent["wavelengths"][0], nrays=3000)
+    gd.propagate(clip=True)
+    gh = ResidentTrace(ps, engine=eng, exact=True)
+    gh.rays_given(gd.y[0], gd.u[0], l=ent["wavelengths"][0])
+    gh.propagate(clip=True)
+    assert np.array_equal(gd.y[-1], gh.y[-1], equal_nan=True)
+    assert np.array_equal(gd.i[0], gd.u[0])
+    for t in (g, g2, gk, gd, gh):
         t.free()
 
 
