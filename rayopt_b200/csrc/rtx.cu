@@ -29,6 +29,7 @@ struct TableSlot {
     void* dev = nullptr;
     cudaEvent_t done = nullptr;
     bool used = false;
+    std::vector<unsigned char> key;  // the rtx_surface bytes + element size this slot holds
 };
 
 struct ChunkBuf {
@@ -134,6 +135,7 @@ int ensure_slots(rtx_ctx* ctx, size_t bytes) {
         CK(cudaMalloc(&sl.dev, nb));
         if (!sl.done) CK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
         sl.used = false;
+        sl.key.clear();
     }
     ctx->slot_bytes = nb;
     return 0;
@@ -215,13 +217,28 @@ int upload_table(rtx_ctx* ctx, const rtx_surface* surf, int S, cudaStream_t stre
     size_t bytes = (size_t)S * sizeof(DevSurf<T>);
     int rc = ensure_slots(ctx, bytes);
     if (rc) return rc;
+    // a table that is already resident (same records, same arithmetic type) is
+    // reused: repeated traces of the same lens / wavelength put no H2D copy
+    // between their kernels
+    const size_t raw = (size_t)S * sizeof(rtx_surface);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(surf);
+    for (auto& sl : ctx->slots) {
+        if (sl.used && sl.key.size() == raw + 1 && sl.key[raw] == (unsigned char)sizeof(T) &&
+            memcmp(sl.key.data(), src, raw) == 0) {
+            *out = reinterpret_cast<const DevSurf<T>*>(sl.dev);
+            return 0;
+        }
+    }
     TableSlot& sl = ctx->slots[ctx->next_slot];
     ctx->next_slot = (ctx->next_slot + 1) % TABLE_SLOTS;
     if (sl.used) CK(cudaEventSynchronize(sl.done));
+    sl.used = false;
     DevSurf<T>* h = reinterpret_cast<DevSurf<T>*>(sl.host);
     for (int i = 0; i < S; ++i) convert_surface<T>(surf[i], h[i]);
     CK(cudaMemcpyAsync(sl.dev, sl.host, bytes, cudaMemcpyHostToDevice, stream));
     CK(cudaEventRecord(sl.done, stream));
+    sl.key.assign(src, src + raw);
+    sl.key.push_back((unsigned char)sizeof(T));
     sl.used = true;
     *out = reinterpret_cast<const DevSurf<T>*>(sl.dev);
     return 0;
