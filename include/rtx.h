@@ -196,6 +196,15 @@ int rtx_trace(rtx_ctx *ctx, const rtx_surface *surf, int S,
 int rtx_set_mask_output(rtx_ctx *ctx, uint32_t *dmask);
 
 /*
+ * Optional per-ray optical path sum for the following rtx_trace calls on
+ * device buffers: dsum (DEVICE, N values of the trace dtype, or NULL = off)
+ * receives sum over traced surfaces 0..upto (inclusive; upto < 0: all) of
+ * t -- the accumulation GeometricTrace.opd starts from
+ * (rayopt/geometric_trace.py:102), without reading the (S,N) array again.
+ */
+int rtx_set_path_sum_output(rtx_ctx *ctx, void *dsum, int upto);
+
+/*
  * Same call with HOST buffers in the reference layout: y0,u0 (N,3);
  * Y,U,I (rows,N,3), T (rows,N) C-contiguous (GeometricTrace.y/u/i/t rows
  * start..stop-1).  Rays are processed in chunks; H2D, kernel and D2H of

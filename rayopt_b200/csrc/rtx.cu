@@ -72,6 +72,8 @@ struct rtx_ctx {
     int lockstep = 1;         // CTA barrier per stored surface (STORE_WARP)
     int max_ctas_per_sm = 0;  // 0: whatever fits
     unsigned* mask = nullptr; // rtx_set_mask_output
+    void* tsum = nullptr;     // rtx_set_path_sum_output
+    int tsum_upto = 0;
     bool tuned = false;       // an RTX_* environment knob overrides the heuristics
     int tune = 1;             // TraceParams::tune bits (RTX_TUNE); 1 = L2 evict_first stores
 };
@@ -338,6 +340,8 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
     p.lockstep = ctx->lockstep;
     p.tune = ctx->tune;
     p.mask = ctx->mask;
+    p.tsum = (T*)ctx->tsum;
+    p.tsum_upto = ctx->tsum_upto < 0 ? S - 1 : ctx->tsum_upto;
     return launch_trace<T>(ctx, p, (flags & RTX_EXACT) != 0, rpt, store, warps, nbuf, stream);
 }
 
@@ -779,19 +783,29 @@ int rtx_trace_host(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* r
     if (dtype != RTX_F64 && dtype != RTX_F32) return RTX_E_BADARG;
     if (N == 0) return 0;
     CK(cudaSetDevice(ctx->device));
-    unsigned* saved = ctx->mask;  // the mask belongs to device-buffer traces
+    unsigned* saved = ctx->mask;  // mask / path sum belong to device-buffer traces
+    void* saved_tsum = ctx->tsum;
     ctx->mask = nullptr;
+    ctx->tsum = nullptr;
     if (dtype == RTX_F64)
         rc = trace_host<double>(ctx, surf, S, rot0, N, y0, u0, clip, keep, Y, U, I, T, flags);
     else
         rc = trace_host<float>(ctx, surf, S, rot0, N, y0, u0, clip, keep, Y, U, I, T, flags);
     ctx->mask = saved;
+    ctx->tsum = saved_tsum;
     return rc;
 }
 
 int rtx_set_mask_output(rtx_ctx* ctx, uint32_t* dmask) {
     if (!ctx) return RTX_E_BADARG;
     ctx->mask = dmask;
+    return 0;
+}
+
+int rtx_set_path_sum_output(rtx_ctx* ctx, void* dsum, int upto) {
+    if (!ctx) return RTX_E_BADARG;
+    ctx->tsum = dsum;
+    ctx->tsum_upto = upto;
     return 0;
 }
 

@@ -169,11 +169,13 @@ class Engine:
                 | {0: 0, 1: RTX_RPT1, 2: RTX_RPT2}[rpt])
 
     def trace_device(self, table, y0, u0, Y, U, I, T, N=None, ld=None, clip=False,
-                     keep_last=False, rot0=None, exact=False, direct=False, rpt=0, mask=None):
+                     keep_last=False, rot0=None, exact=False, direct=False, rpt=0, mask=None,
+                     path_sum=None, path_sum_upto=-1):
         """One launch on DEVICE arrays (DeviceArray or None for outputs).
         Asynchronous on the engine stream.  `mask`: optional uint32
         DeviceArray of ceil(N/32) words receiving the warp-ballot vignetting
-        mask (bit set = the ray survives the last surface)."""
+        mask (bit set = the ray survives the last surface).  `path_sum`:
+        optional (N,) DeviceArray receiving sum_{s <= path_sum_upto} t[s]."""
         table = self._table(table)
         dt = _code(y0.dtype)
         N = y0.shape[0] if N is None else int(N)
@@ -182,9 +184,10 @@ class Engine:
             ld = first.shape[1] if first is not None else (N + 63)//64*64
         r0 = None if rot0 is None else np.ascontiguousarray(rot0, np.float64).reshape(9)
         dp = lambda a: None if a is None else a.ptr  # noqa: E731
-        if mask is None and all(a is None for a in (Y, U, I, T)):
-            raise ValueError("nothing to store: pass an output array or a mask")
+        if mask is None and path_sum is None and all(a is None for a in (Y, U, I, T)):
+            raise ValueError("nothing to store: pass an output array, a mask or a path sum")
         check(self.lib.rtx_set_mask_output(self.ctx, dp(mask)))
+        check(self.lib.rtx_set_path_sum_output(self.ctx, dp(path_sum), int(path_sum_upto)))
         check(self.lib.rtx_trace(
             self.ctx, ptr(table), len(table), ptr(r0), dt, N, y0.ptr, u0.ptr,
             int(bool(clip)), RTX_KEEP_LAST if keep_last else RTX_KEEP_ALL, ld,

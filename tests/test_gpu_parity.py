@@ -503,3 +503,21 @@ def test_device_ray_generation(eng, systems):
     eng.sync()
     want = np_oracle.trace(table, hy, hu, clip=True)[0]
     assert_parity(Y.download()[:, :n], want, FP64_RTOL, "device-generated bundle")
+
+
+def test_path_sum_output(eng):
+    """rtx_set_path_sum_output: per-ray sum of the optical path over the
+    first surfaces, as GeometricTrace.opd accumulates it (geometric_trace.py:102)"""
+    c = load_golden("zoom_f1_clip")
+    n, S = c["y0"].shape[0], len(c["table"])
+    d_y0, d_u0 = eng.to_device(c["y0"]), eng.to_device(c["u0"])
+    acc = eng.empty((n,))
+    for upto in (-1, S - 3, 0):
+        eng.trace_device(c["table"], d_y0, d_u0, None, None, None, None, N=n, clip=True,
+                         exact=True, path_sum=acc, path_sum_upto=upto)
+        eng.sync()
+        k = S if upto < 0 else upto + 1
+        want = np.zeros(n)
+        for j in range(k):                 # same left-to-right order as the kernel
+            want = want + c["T"][j]
+        assert np.array_equal(acc.download(), want, equal_nan=True), upto
