@@ -70,11 +70,8 @@ with np.errstate(all="ignore"):
 xy[idx == 0] = 0
 hy, hu = aim_infinite(aim_p["field"], xy, aim_p["z"], aim_p["p"], ent["object_angle"])
 want = np_oracle.trace(table, hy, hu, clip=True)[0][-1]
-seg = pg.buf.rows(0)  # whole buffer view
 got = np.empty((len(idx), 3))
-full = None
-# download only the sampled rows (one small D2H per ray would be slow: fetch a window per index)
-from rayopt_b200._lib import check, ptr
+from rayopt_b200._lib import check, ptr          # 24-byte D2H per sampled ray
 for j, ii in enumerate(idx):
     row = np.empty(3)
     check(eng.lib.rtx_memcpy_d2h(eng.ctx, ptr(row), pg.buf.ptr + (pg.b[peer] + int(ii))*24, 24))
