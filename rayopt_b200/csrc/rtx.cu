@@ -334,9 +334,17 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
         warps = 8;
         nbuf = 2;
     }
-    const bool bulk_ok = !(flags & RTX_STORE_DIRECT) && (ld % (32 * rpt) == 0) && al16(Y) &&
-                         al16(U) && al16(I) && al16(Tt) && peers_ok;
-    if (!bulk_ok) store = STORE_DIRECT;
+    const bool aligned = !(flags & RTX_STORE_DIRECT) && al16(Y) && al16(U) && al16(I) && al16(Tt) &&
+                         peers_ok;
+    if (aligned && ld % (32 * rpt) != 0 && ld % 32 == 0) {
+        // a pitch of whole 32-ray groups only: the one-ray-per-thread
+        // per-warp bulk-store kernel still applies
+        rpt = 1;
+        store = STORE_WARP;
+        warps = 8;
+        nbuf = 2;
+    }
+    if (!(aligned && ld % (32 * rpt) == 0)) store = STORE_DIRECT;
     p.lockstep = ctx->lockstep;
     p.tune = ctx->tune;
     p.mask = ctx->mask;
