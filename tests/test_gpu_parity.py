@@ -521,3 +521,25 @@ def test_path_sum_output(eng):
         for j in range(k):                 # same left-to-right order as the kernel
             want = want + c["T"][j]
         assert np.array_equal(acc.download(), want, equal_nan=True), upto
+
+
+def test_pitch_of_32_ray_groups(eng, systems):
+    """ld a multiple of 32 but not of 64, N > 32768: one-ray-per-thread bulk
+    stores; same rows as the default configuration"""
+    ent = systems["zoom"]
+    table, aim = ent["tables"][0], ent["aim"][0][1]
+    n = 40000
+    y0, u0 = aim_infinite(aim["field"], disc(n, 6), aim["z"], aim["p"], ent["object_angle"])
+    d_y0, d_u0 = eng.to_device(y0), eng.to_device(u0)
+    S = len(table)
+    out = {}
+    for ld in (40032, 40064):
+        Y, T = eng.empty((S, ld, 3)), eng.empty((S, ld))
+        eng.trace_device(table, d_y0, d_u0, Y, None, None, T, N=n, ld=ld, clip=True, exact=True)
+        eng.sync()
+        out[ld] = (Y.download()[:, :n], T.download()[:, :n])
+        Y.free(), T.free()
+    for a, b in zip(out[40032], out[40064]):
+        assert np.array_equal(a, b, equal_nan=True)
+    want = np_oracle.trace(table, y0, u0, clip=True)
+    assert np.array_equal(out[40032][0], want[0], equal_nan=True)
