@@ -250,3 +250,67 @@ def test_reference_own_raytrace_tests_through_the_dropin():
     z1, p1 = s.pupil((0, 1.))
     np.testing.assert_allclose(z1, z0, rtol=1e-12)
     np.testing.assert_allclose(p1, p0, rtol=1e-12)
+
+
+class FakeDeviceArray:
+    """numpy-backed stand-in for rayopt_b200.engine.DeviceArray"""
+
+    def __init__(self, a):
+        self.a = a
+        self.shape, self.dtype, self.nbytes = a.shape, a.dtype, a.nbytes
+        self.downloads = 0
+
+    def rows(self, r0, r1=None):
+        return FakeDeviceArray(self.a[r0:(r0 + 1 if r1 is None else r1)])
+
+    def upload(self, v):
+        self.a[...] = np.asarray(v).reshape(self.a.shape)
+        return self
+
+    def download(self, out=None):
+        return self.a.copy()
+
+    def free(self):
+        pass
+
+
+class FakeResidentEngine:
+    def empty(self, shape, dtype=np.float64):
+        return FakeDeviceArray(np.full(shape, np.nan, dtype))
+
+    def to_device(self, a, dtype=None):
+        return FakeDeviceArray(np.array(a, dtype))
+
+    def trace_device(self, table, y0, u0, Y, U, I, T, N=None, ld=None, clip=False, rot0=None,
+                     exact=False, **kw):
+        res = np_oracle.trace(table, y0.a[0, :N], u0.a[0, :N], clip=clip, rot0=rot0)
+        for dst, src in zip((Y, U, I, T), res):
+            dst.a[:, :N] = src
+
+    def rms(self, y, w, N=None, ref_point=None):
+        return np_oracle.rms(y.a[0, :N], None if w is None else w.a,
+                             ref=None) if ref_point is None else float("nan")
+
+
+def test_resident_trace_host_logic_on_cpu():
+    """LazyRows / ResidentTrace bookkeeping (row cache, invalidation on
+    re-propagate, sub-range traces from a resident row) without a GPU"""
+    from rayopt_b200 import ResidentTrace
+    ps, ent = _packed("double_gauss")
+    c = load_golden("double_gauss_l0_clip")
+    g = ResidentTrace(ps, engine=FakeResidentEngine())
+    g.rays_given(c["y0"][:, :2] if False else c["y0"], c["u0"], l=ent["wavelengths"][0], w=c["w"])
+    g.propagate(clip=True)
+    assert g.y.shape == (13, 256, 3) and g.t.shape == (13, 256) and len(g.y) == 13
+    assert np.array_equal(g.y[-1], c["Y"][-1], equal_nan=True)
+    assert np.array_equal(g.y[5, :, :2], c["Y"][4, :, :2], equal_nan=True)
+    assert np.array_equal(g.u[2:4], c["U"][1:3], equal_nan=True)
+    assert np.array_equal(np.asarray(g.t)[1:], c["T"], equal_nan=True)
+    assert np.array_equal(g.i[0], c["u0"]) and np.array_equal(g.n[1:], c["n"])
+    first = g.y[-1]
+    assert g.y[-1] is first                      # cached row
+    g.propagate(start=4, stop=9, clip=False)     # rows 4..8 re-traced, cache dropped
+    assert g.y[-1] is first and 5 not in g.y._rows
+    want = np_oracle.trace(c["table"][3:8], g.y[3], g.u[3], clip=False)
+    assert np.array_equal(g.y[4:9], want[0], equal_nan=True)
+    assert abs(g.rms(3) - np_oracle.rms(g.y[3], c["w"])) < 1e-15
