@@ -275,6 +275,13 @@ class Engine:
                                         rings, ptr(frame), pmax, y0.ptr, u0.ptr))
         return y0, u0
 
+    def aim_infinite_into(self, y_dst, u_dst, count, rings, frame, pmax, yp=None):
+        """rtx_aim_infinite into existing device rows (DeviceArray views)"""
+        frame = np.ascontiguousarray(frame, np.float64)
+        check(self.lib.rtx_aim_infinite(self.ctx, _code(y_dst.dtype), int(count),
+                                        None if yp is None else yp.ptr, int(rings), ptr(frame),
+                                        float(pmax), y_dst.ptr, u_dst.ptr))
+
     def selftest_math(self, a, b):
         """(6, n): engine a/b, IEEE a/b, engine sqrt(a), IEEE sqrt(a),
         engine 1/sqrt(a), IEEE 1/sqrt(a)"""

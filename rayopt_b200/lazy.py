@@ -139,7 +139,6 @@ class ResidentTrace:
         hexapolar grid with about `nrays` rays, or the DEVICE pupil coordinates
         `yp` (N,2); (z, p) is the reference's pupil-aiming solution
         (System.pupil).  Nothing crosses PCIe."""
-        from ._lib import check, ptr
         from .rays import aim_frame
         eng = self.engine
         if yp is None:
@@ -152,16 +151,40 @@ class ResidentTrace:
         self.l = self.system.wavelengths[0] if l is None else l
         self.w = np.full(count, 1./count)
         self.ref = ref
-        frame = np.ascontiguousarray(np.concatenate(aim_frame(yo, z, angle)), np.float64)
+        frame = np.concatenate(aim_frame(yo, z, angle))
         pmax = float(np.fabs(np.asarray(p, float)).max())
         for dst in ("u", "i"):           # i[0] = u[0] (geometric_trace.py:68)
-            check(eng.lib.rtx_aim_infinite(eng.ctx, 0, count, None if yp is None else yp.ptr,
-                                           rings, ptr(frame), pmax, self._dev["y"].rows(0).ptr,
-                                           self._dev[dst].rows(0).ptr))
+            eng.aim_infinite_into(self._dev["y"].rows(0), self._dev[dst].rows(0), count, rings,
+                                  frame, pmax, yp)
         self._dev["t"].rows(0).upload(np.zeros(self._ld))
         for a in (self.y, self.u, self.i, self.t):
             a.invalidate()
         self.n[0] = self.system.refractive_index(self.l, 0)
+
+    def rays_point(self, yo, wavelength=None, nrays=11, distribution="hexapolar",
+                   filter=None, stop=None, clip=False):
+        """GeometricTrace.rays_point (rayopt/geometric_trace.py:204-209) for a
+        rayopt ``System``: the pupil is aimed by the reference on the host
+        (``system.pupil``); for an infinite rectilinear object with a plane
+        first surface and the hexapolar distribution the rays are then
+        generated in HBM, otherwise by ``system.aim`` on the host and
+        uploaded.  Traces with `clip`."""
+        s = self.system
+        l = s.wavelengths[0] if wavelength is None else wavelength
+        z, p = s.pupil(yo, l=wavelength, stop=stop)
+        obj = s.object
+        on_device = (distribution == "hexapolar" and not obj.finite and nrays > 1 and
+                     getattr(obj, "projection", "rectilinear") == "rectilinear" and
+                     not getattr(s[0], "curvature", 0.) and
+                     getattr(s[0], "aspherics", None) is None and filter in (None, False) and clip)
+        if on_device:
+            self.rays_infinite(yo, z, p, obj.angle, l=l, nrays=nrays)
+        else:
+            from rayopt.utils import pupil_distribution      # the reference's own helper
+            ref, yp, weight = pupil_distribution(distribution, nrays)
+            y, u = s.aim(yo, yp, z, p, filter=(not clip) if filter is None else filter)
+            self.rays_given(y, u, l, weight, ref)
+        self.propagate(clip=clip)
 
     def propagate(self, start=1, stop=None, clip=False):
         init = start - 1

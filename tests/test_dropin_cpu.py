@@ -314,3 +314,38 @@ def test_resident_trace_host_logic_on_cpu():
     want = np_oracle.trace(c["table"][3:8], g.y[3], g.u[3], clip=False)
     assert np.array_equal(g.y[4:9], want[0], equal_nan=True)
     assert abs(g.rms(3) - np_oracle.rms(g.y[3], c["w"])) < 1e-15
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+def test_resident_rays_point_matches_reference():
+    """ResidentTrace.rays_point on a reference System: host aiming by the
+    reference, hexapolar rays "generated on the device" (here: the host
+    restatement behind the fake engine) -- same trace as the reference's
+    rays_point; other distributions go through system.aim"""
+    warnings.simplefilter("ignore")
+    R = ref_shim.load()
+    from rayopt_b200 import ResidentTrace
+    from rayopt_b200.rays import aim_infinite, hexapolar
+
+    class Eng(FakeResidentEngine):
+        def aim_infinite_into(self, y_dst, u_dst, count, rings, frame, pmax, yp=None):
+            assert yp is None
+            xy = hexapolar(count)[1]
+            u, yb, s_, m = (np.asarray(frame[3*k:3*k + 3]) for k in range(4))
+            y = yb + ((xy[:, 0, None]*pmax)*s_ + (xy[:, 1, None]*pmax)*m)
+            y = y + (-y[:, 2]/u[2])[:, None]*u
+            y_dst.a[0, :count], u_dst.a[0, :count] = y, u
+    s = R.System(**yaml.safe_load(systems_yaml.DOUBLE_GAUSS))
+    s.update()
+    s.paraxial.refocus()
+    ref = R.GeometricTrace(s)
+    ref.rays_point((0, .7), nrays=500, distribution="hexapolar", clip=True)
+    got = ResidentTrace(s, engine=Eng())
+    got.rays_point((0, .7), nrays=500, distribution="hexapolar", clip=True)
+    assert got.nrays == ref.y.shape[1]
+    np.testing.assert_allclose(got.y[0], ref.y[0], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(np.asarray(got.y), ref.y, rtol=0, atol=1e-11)
+    assert np.array_equal(np.isnan(np.asarray(got.u)), np.isnan(ref.u))
+    ref.rays_point((0, 1.), nrays=60, distribution="square", clip=False)
+    got.rays_point((0, 1.), nrays=60, distribution="square", clip=False)
+    assert np.array_equal(np.asarray(got.y), ref.y, equal_nan=True)
