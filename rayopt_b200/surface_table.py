@@ -113,15 +113,64 @@ def pack_system(system, l, start=1, stop=None, n0=None):
     if hasattr(system, "pack"):                # pre-packed (PackedSystem)
         return system.pack(l, start, stop, n0)
     elements = list(system[start:stop])
-    if len(elements) > RTX_MAX_SURFACES:
-        raise ValueError("too many surfaces: %d" % len(elements))
+    S = len(elements)
+    if S > RTX_MAX_SURFACES:
+        raise ValueError("too many surfaces: %d" % S)
     if n0 is None:
         n0 = system.refractive_index(l, start - 1)
-    table = np.zeros(len(elements), SURFACE_DTYPE)
-    n = np.empty(len(elements))
+    # column-wise fill (the record-by-record pack_element is ~13 us per
+    # surface in numpy scalar assignments; aiming issues hundreds of tiny
+    # traces, rayopt/system.py:507-555).  Same expressions as pack_element.
+    table = np.zeros(S, SURFACE_DTYPE)
+    n = np.empty(S)
+    off, rot, cs, ks, kc2, rad2, mus, n0s, flags, nas = [], [], [], [], [], [], [], [], [], []
+    eye = (1., 0., 0., 0., 1., 0., 0., 0., 1.)
     for j, e in enumerate(elements):
-        n0 = pack_element(table[j], e, n0, l)
-        n[j] = n0
+        off.append(e.offset)
+        f = 0
+        if getattr(e, "rotated", False):
+            f |= F_ROTATED
+            rot.append(np.asarray(e.rot_normal, float).reshape(9))
+        else:
+            rot.append(eye)
+        c = getattr(e, "curvature", 0.)
+        k = getattr(e, "conic", 0.)
+        if getattr(e, "alternate_intersection", False):
+            f |= F_ALT
+        cs.append(c)
+        ks.append(k)
+        kc2.append((1 + k)*c**2)                           # elements.py:448,467
+        radius = getattr(e, "radius", np.inf)
+        rad2.append(radius**2)                             # elements.py:207
+        nn, mu = get_n_mu(e, n0, l)
+        if not mu:                                         # elements.py:313
+            mu = 1.
+        mus.append(mu)
+        n0s.append(n0)
+        n[j] = n0 = nn
+        flags.append(f)
+        asph = getattr(e, "aspherics", None)
+        if asph is None:
+            nas.append(-1)
+        else:
+            asph = list(asph)
+            if len(asph) > RTX_MAX_ASPH:
+                raise ValueError("at most %d aspheric coefficients are supported, "
+                                 "got %d" % (RTX_MAX_ASPH, len(asph)))
+            nas.append(len(asph))
+            for i, a in enumerate(asph):
+                table["asph"][j, i] = a
+                table["dasph"][j, i] = 2*(i + 1)*a         # elements.py:472
+    if S:
+        table["offset"] = off
+        table["rot"] = rot
+        table["c"], table["k"], table["kc2"], table["radius2"] = cs, ks, kc2, rad2
+        table["mu"] = mus
+        table["muf"] = [abs(m) for m in mus]               # elements.py:360
+        table["sgn"] = [np.sign(m) for m in mus]           # elements.py:367
+        table["mu2m1"] = [m**2 - 1 for m in mus]           # elements.py:366
+        table["n0"], table["n"] = n0s, n
+        table["n_asph"], table["flags"] = nas, flags
     init = system[start - 1]
     rot0 = None
     if getattr(init, "rotated", False):
