@@ -32,11 +32,17 @@ Y, U, I = (mem.empty((S, ld, 3), dt) for _ in range(3))
 T = mem.empty((S, ld), dt)
 alg = N*(6*w + 10*w*S)
 for cfg in a.cfgs:
-    parts = [int(x) for x in cfg.split(",")]
+    if cfg == "default":          # the library's own heuristics (no RTX_* knob set)
+        for k in ("RTX_RPT", "RTX_STORE", "RTX_WARPS", "RTX_NBUF", "RTX_LOCK", "RTX_MAX_CTAS", "RTX_TUNE"):
+            os.environ.pop(k, None)
+        parts = [0, 0, 0, 0, 0, 0, -1]
+    else:
+        parts = [int(x) for x in cfg.split(",")]
     rpt, store, warps, nbuf, lock, maxc = parts[:6]
     tune = parts[6] if len(parts) > 6 else 0
-    os.environ["RTX_TUNE"] = str(tune)
-    os.environ.update(RTX_RPT=str(rpt), RTX_STORE=str(store), RTX_WARPS=str(warps),
+    if cfg != "default":
+        os.environ["RTX_TUNE"] = str(tune)
+        os.environ.update(RTX_RPT=str(rpt), RTX_STORE=str(store), RTX_WARPS=str(warps),
                       RTX_NBUF=str(nbuf), RTX_LOCK=str(lock), RTX_MAX_CTAS=str(maxc))
     e = Engine(0)
     ms = []
