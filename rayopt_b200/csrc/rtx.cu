@@ -304,19 +304,21 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
     if (flags & RTX_RPT1) rpt = 1;
     if (flags & RTX_RPT2) rpt = 2;
     int store = ctx->store, warps = ctx->warps, nbuf = ctx->nbuf;
+    bool heavy = false;
     if (!ctx->tuned) {
         // measured best configurations (profiles/r1_sweep8_defaults.txt):
         //  FP64: 16 warps x 2 rays, per-CTA bulk stores (24 KB runs)      0.94
         //  FP32: 32 warps x 2 rays (24 KB runs again)                     0.90
         //  systems with >= 25 % Newton (aspheric) surfaces are bound by the
         //  FP64/FP32 pipes and divergent iteration counts, not by HBM: small
-        //  8-warp CTAs with per-warp stores (more independent CTAs per SM),
-        //  1 ray per thread in FP64 (64 registers), 2 in FP32
+        //  8-warp CTAs, 2 rays per thread, per-warp stores and NO lockstep
+        //  (free-running warps hide the long dependent chains: 0.69 vs 0.60
+        //  in FP64, 0.63 vs 0.58 in FP32, profiles/r1_sweep12_asph_lockstep.txt)
         int newton = 0;
         for (int i = 0; i < S; ++i) newton += surf && surf[i].n_asph >= 0;
-        const bool heavy = newton * 4 >= S;
+        heavy = newton * 4 >= S;
         if (heavy && !(flags & (RTX_RPT1 | RTX_RPT2))) {
-            rpt = sizeof(T) == 4 ? 2 : 1;
+            rpt = 2;
             store = STORE_WARP;
             warps = 8;
             nbuf = 2;
@@ -345,7 +347,7 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
         nbuf = 2;
     }
     if (!(aligned && ld % (32 * rpt) == 0)) store = STORE_DIRECT;
-    p.lockstep = ctx->lockstep;
+    p.lockstep = heavy ? 0 : ctx->lockstep;
     p.tune = ctx->tune;
     p.mask = ctx->mask;
     p.tsum = (T*)ctx->tsum;
