@@ -4,7 +4,6 @@ raises at context creation."""
 import ctypes as C
 import os
 
-import numpy as np
 
 from .surface_table import SURFACE_DTYPE
 

@@ -6,7 +6,7 @@ usage: python scripts/sweep.py [--rays N] [--exact 0|1] cfg1 cfg2 ...
        cfg = rpt,store,warps,nbuf,lock,maxctas   e.g. 2,1,8,2,1,0
        (store 1: per-warp bulk stores, 2: per-CTA bulk stores)
 Build with RTX_TUNING_SPACE=1 for the full variant space."""
-import argparse, json, os, statistics, sys
+import argparse, os, statistics, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -19,7 +19,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
 import torch, torch.distributed as dist
 import np_oracle, bench
 from rayopt_b200.engine import Engine
-from rayopt_b200.rays import aim_infinite, hexapolar
+from rayopt_b200.rays import aim_infinite
 from rayopt_b200.sharding import PeerGather
 
 local = int(os.environ.get("LOCAL_RANK", "0"))

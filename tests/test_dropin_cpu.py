@@ -325,7 +325,7 @@ def test_resident_rays_point_matches_reference():
     warnings.simplefilter("ignore")
     R = ref_shim.load()
     from rayopt_b200 import ResidentTrace
-    from rayopt_b200.rays import aim_infinite, hexapolar
+    from rayopt_b200.rays import hexapolar
 
     class Eng(FakeResidentEngine):
         def aim_infinite_into(self, y_dst, u_dst, count, rings, frame, pmax, yp=None):

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import np_oracle
-from conftest import golden_names, load_golden, load_systems, assert_parity
+from conftest import golden_names, load_golden, assert_parity
 from rayopt_b200.rays import aim_infinite, disc
 
 pytestmark = pytest.mark.gpu

@@ -1,6 +1,5 @@
 """Host logic: table packer and the launch-ray generator (CPU)."""
 import json
-import warnings
 
 import numpy as np
 import pytest
