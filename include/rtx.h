@@ -186,6 +186,22 @@ int rtx_trace(rtx_ctx *ctx, const rtx_surface *surf, int S,
               void *Y, void *U, void *I, void *T, unsigned flags);
 
 /*
+ * Batched bundles: nb <= RTX_MAX_BATCH bundles of the SAME lens
+ * (S surfaces each) -- typically one per wavelength or field: surf[b] its
+ * table, N[b] its rays, y0[b], u0[b], Y[b].. its DEVICE arrays (rows x ld
+ * pitch shared; Y, U, I, T may each be NULL as a whole) -- marched by ONE
+ * launch: the persistent CTAs walk a launch-wide tile list and re-stage the
+ * surface table (TMA) when they cross into the next bundle.  Removes the
+ * kernel boundaries between the wavelength traces of one analysis step.
+ */
+#define RTX_MAX_BATCH 8
+int rtx_trace_batch(rtx_ctx *ctx, int nb, const rtx_surface *const *surf, int S,
+                    const double *rot0, int dtype, const int64_t *N,
+                    const void *const *y0, const void *const *u0, int clip,
+                    int keep, int64_t ld, void *const *Y, void *const *U,
+                    void *const *I, void *const *T, unsigned flags);
+
+/*
  * Optional warp-ballot vignetting mask for the following rtx_trace /
  * rtx_trace_gather calls on device buffers: dmask (DEVICE, ceil(N/32) words,
  * or NULL to switch it off) receives bit (ray % 32) of word ray / 32 = 1 when

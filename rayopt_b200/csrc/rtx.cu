@@ -156,11 +156,17 @@ int launch_one(rtx_ctx* ctx, const TraceParams<T>& p, cudaStream_t stream) {
     if (occ < 1) occ = 1;
     if (ctx->max_ctas_per_sm > 0 && occ > ctx->max_ctas_per_sm) occ = ctx->max_ctas_per_sm;
     const long long per_cta = (long long)threads * RPT;
-    long long tiles = (p.N + per_cta - 1) / per_cta;
+    TraceParams<T> q = p;  // launch-wide CTA-tile numbering over the bundles
+    long long tiles = 0;
+    for (int b = 0; b < q.nbatch; ++b) {
+        q.item[b].tile0 = tiles;
+        tiles += (q.item[b].N + per_cta - 1) / per_cta;
+    }
+    q.total_tiles = tiles;
     long long grid = (long long)ctx->sm_count * occ;  // persistent: one wave
     if (grid > tiles) grid = tiles;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, threads, smem, stream>>>(p);
+    kern<<<(unsigned)grid, threads, smem, stream>>>(q);
     ctx->launches++;
     return (int)cudaGetLastError();
 }
@@ -215,7 +221,7 @@ int launch_trace<float>(rtx_ctx* ctx, const TraceParams<float>& p, bool exact, i
 // ordered on `stream`; the pinned slot is recycled only after its copy ran.
 template <typename T>
 int upload_table(rtx_ctx* ctx, const rtx_surface* surf, int S, cudaStream_t stream,
-                 const DevSurf<T>** out) {
+                 const DevSurf<T>** out, const void* const* keep = nullptr, int nkeep = 0) {
     size_t bytes = (size_t)S * sizeof(DevSurf<T>);
     int rc = ensure_slots(ctx, bytes);
     if (rc) return rc;
@@ -231,8 +237,17 @@ int upload_table(rtx_ctx* ctx, const rtx_surface* surf, int S, cudaStream_t stre
             return 0;
         }
     }
-    TableSlot& sl = ctx->slots[ctx->next_slot];
-    ctx->next_slot = (ctx->next_slot + 1) % TABLE_SLOTS;
+    // next slot in the ring that holds none of the tables the caller still
+    // needs (the other bundles of a batched launch)
+    int pick = ctx->next_slot;
+    for (int tries = 0; tries < TABLE_SLOTS; ++tries) {
+        bool busy = false;
+        for (int k = 0; k < nkeep; ++k) busy = busy || keep[k] == ctx->slots[pick].dev;
+        if (!busy) break;
+        pick = (pick + 1) % TABLE_SLOTS;
+    }
+    TableSlot& sl = ctx->slots[pick];
+    ctx->next_slot = (pick + 1) % TABLE_SLOTS;
     if (sl.used) CK(cudaEventSynchronize(sl.done));
     sl.used = false;
     DevSurf<T>* h = reinterpret_cast<DevSurf<T>*>(sl.host);
@@ -255,6 +270,12 @@ int check_table(const rtx_surface* surf, int S) {
     return 0;
 }
 
+template <typename T>
+struct Batch {
+    int n = 0;
+    BatchItem<T> item[RTX_MAX_BATCH];
+};
+
 struct PeerDst {
     int n = 0;
     long long off = 0;
@@ -266,7 +287,7 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
                  const void* y0, const void* u0, int clip, int keep, long long ld, void* Y,
                  void* U, void* I, void* Tt, unsigned flags, cudaStream_t stream,
                  const DevSurf<T>* table /* may be null: upload */,
-                 const PeerDst* peers = nullptr) {
+                 const PeerDst* peers = nullptr, const Batch<T>* batch = nullptr) {
     if (!table) {
         int rc = upload_table<T>(ctx, surf, S, stream, &table);
         if (rc) return rc;
@@ -347,6 +368,20 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
         nbuf = 2;
     }
     if (!(aligned && ld % (32 * rpt) == 0)) store = STORE_DIRECT;
+    if (batch && batch->n > 0) {
+        p.nbatch = batch->n;
+        for (int b = 0; b < batch->n; ++b) p.item[b] = batch->item[b];
+    } else {
+        p.nbatch = 1;
+        p.item[0].table = table;
+        p.item[0].y0 = p.y0;
+        p.item[0].u0 = p.u0;
+        p.item[0].Y = p.Y;
+        p.item[0].U = p.U;
+        p.item[0].I = p.I;
+        p.item[0].Tt = p.Tt;
+        p.item[0].N = N;
+    }
     p.lockstep = heavy ? 0 : ctx->lockstep;
     p.tune = ctx->tune;
     p.mask = ctx->mask;
@@ -776,6 +811,77 @@ int rtx_trace(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0, 
     else
         rc = trace_device<float>(ctx, surf, S, rot0, N, y0, u0, clip, keep, ld, Y, U, I, T, flags,
                                  ctx->stream, nullptr);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->k1, ctx->stream));
+    ctx->kernel_timed = true;
+    return 0;
+}
+
+}  // extern "C"
+
+namespace {
+template <typename T>
+int trace_batch(rtx_ctx* ctx, int nb, const rtx_surface* const* surf, int S, const double* rot0,
+                const int64_t* N, const void* const* y0, const void* const* u0, int clip, int keep,
+                long long ld, void* const* Y, void* const* U, void* const* I, void* const* Tt,
+                unsigned flags) {
+    Batch<T> bt;
+    const void* tabs[RTX_MAX_BATCH];
+    long long nmax = 0;
+    for (int b = 0; b < nb; ++b) {
+        const DevSurf<T>* tab = nullptr;
+        int rc = upload_table<T>(ctx, surf[b], S, ctx->stream, &tab, tabs, bt.n);
+        if (rc) return rc;
+        tabs[bt.n] = tab;
+        BatchItem<T>& it = bt.item[bt.n++];
+        it.table = tab;
+        it.y0 = (const T*)y0[b];
+        it.u0 = (const T*)u0[b];
+        it.Y = Y ? (T*)Y[b] : nullptr;
+        it.U = U ? (T*)U[b] : nullptr;
+        it.I = I ? (T*)I[b] : nullptr;
+        it.Tt = Tt ? (T*)Tt[b] : nullptr;
+        it.N = N[b];
+        it.tile0 = 0;
+        if (N[b] > nmax) nmax = N[b];
+        // every bundle must satisfy the alignment the bulk-store path needs
+        for (void* q : {(void*)it.Y, (void*)it.U, (void*)it.I, (void*)it.Tt})
+            if (reinterpret_cast<uintptr_t>(q) & 15u) flags |= RTX_STORE_DIRECT;
+    }
+    // kernel configuration from the first bundle (same lens), N of the largest
+    return trace_device<T>(ctx, surf[0], S, rot0, nmax, y0[0], u0[0], clip, keep, ld,
+                           Y ? Y[0] : nullptr, U ? U[0] : nullptr, I ? I[0] : nullptr,
+                           Tt ? Tt[0] : nullptr, flags, ctx->stream, bt.item[0].table, nullptr, &bt);
+}
+}  // namespace
+
+extern "C" {
+
+int rtx_trace_batch(rtx_ctx* ctx, int nb, const rtx_surface* const* surf, int S,
+                    const double* rot0, int dtype, const int64_t* N, const void* const* y0,
+                    const void* const* u0, int clip, int keep, int64_t ld, void* const* Y,
+                    void* const* U, void* const* I, void* const* T, unsigned flags) {
+    if (!ctx || nb < 1 || nb > RTX_MAX_BATCH || !surf || !N || !y0 || !u0) return RTX_E_BADARG;
+    if (keep != RTX_KEEP_ALL && keep != RTX_KEEP_LAST) return RTX_E_BADARG;
+    if (dtype != RTX_F64 && dtype != RTX_F32) return RTX_E_BADARG;
+    for (int b = 0; b < nb; ++b) {
+        int rc = check_table(surf[b], S);
+        if (rc) return rc;
+        if (N[b] < 1 || ld < N[b] || !y0[b] || !u0[b]) return RTX_E_BADARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    unsigned* saved_mask = ctx->mask;  // per-ray side outputs are single-bundle features
+    void* saved_tsum = ctx->tsum;
+    ctx->mask = nullptr;
+    ctx->tsum = nullptr;
+    CK(cudaEventRecord(ctx->k0, ctx->stream));
+    int rc = dtype == RTX_F64
+                 ? trace_batch<double>(ctx, nb, surf, S, rot0, N, y0, u0, clip, keep, ld, Y, U, I,
+                                       T, flags)
+                 : trace_batch<float>(ctx, nb, surf, S, rot0, N, y0, u0, clip, keep, ld, Y, U, I, T,
+                                      flags);
+    ctx->mask = saved_mask;
+    ctx->tsum = saved_tsum;
     if (rc) return rc;
     CK(cudaEventRecord(ctx->k1, ctx->stream));
     ctx->kernel_timed = true;

@@ -193,6 +193,36 @@ class Engine:
             int(bool(clip)), RTX_KEEP_LAST if keep_last else RTX_KEEP_ALL, ld,
             dp(Y), dp(U), dp(I), dp(T), self._flags(exact, direct, rpt)))
 
+    def trace_device_batch(self, tables, y0s, u0s, Ys, Us, Is, Ts, Ns=None, ld=None, clip=False,
+                           keep_last=False, rot0=None, exact=False):
+        """rtx_trace_batch: several bundles of the same lens (one table each,
+        e.g. one per wavelength) in ONE launch.  Lists of DeviceArrays (any of
+        Ys/Us/Is/Ts may be None as a whole)."""
+        nb = len(tables)
+        tabs = [self._table(t) for t in tables]
+        S = len(tabs[0])
+        if any(len(t) != S for t in tabs):
+            raise ValueError("all bundles of a batch must have the same number of surfaces")
+        dt = _code(y0s[0].dtype)
+        Ns = [a.shape[0] for a in y0s] if Ns is None else [int(n) for n in Ns]
+        first = next(a for a in (Ys, Us, Is, Ts) if a is not None)[0]
+        ld = first.shape[1] if ld is None else int(ld)
+        vp = C.c_void_p
+
+        def arr(items, get):
+            if items is None:
+                return None
+            return (vp*nb)(*[vp(get(x)) for x in items])
+        a_tab = arr(tabs, lambda t: t.ctypes.data)
+        a_n = (C.c_int64*nb)(*Ns)
+        r0 = None if rot0 is None else np.ascontiguousarray(rot0, np.float64).reshape(9)
+        check(self.lib.rtx_trace_batch(
+            self.ctx, nb, C.cast(a_tab, vp), S, ptr(r0), dt, C.cast(a_n, vp),
+            C.cast(arr(y0s, lambda a: a.ptr), vp), C.cast(arr(u0s, lambda a: a.ptr), vp),
+            int(bool(clip)), RTX_KEEP_LAST if keep_last else RTX_KEEP_ALL, ld,
+            *[None if x is None else C.cast(arr(x, lambda a: a.ptr), vp) for x in (Ys, Us, Is, Ts)],
+            self._flags(exact, False)))
+
     def trace(self, table, y0, u0, clip=False, keep_last=False, rot0=None,
               dtype=np.float64, exact=False, direct=False, rpt=0, out=None,
               want=("y", "u", "i", "t")):

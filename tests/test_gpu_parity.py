@@ -543,3 +543,33 @@ def test_pitch_of_32_ray_groups(eng, systems):
         assert np.array_equal(a, b, equal_nan=True)
     want = np_oracle.trace(table, y0, u0, clip=True)
     assert np.array_equal(out[40032][0], want[0], equal_nan=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_batched_bundles_one_launch(eng, systems, dtype):
+    """rtx_trace_batch: three wavelength bundles of different (ragged) sizes in
+    ONE launch give exactly the arrays of three separate launches"""
+    ent = systems["double_gauss"]
+    ns = [70001, 40000, 99999]
+    S = ent["S"]
+    ld = (max(ns) + 63)//64*64
+    rays, single, outs = [], [], []
+    for li, n in enumerate(ns):
+        aim = ent["aim"][li][3]
+        y0, u0 = aim_infinite(aim["field"], disc(n, 20 + li), aim["z"], aim["p"], ent["object_angle"])
+        d = (eng.to_device(y0, dtype), eng.to_device(u0, dtype))
+        rays.append(d)
+        ref = [eng.empty((S, ld, 3), dtype) for _ in range(3)] + [eng.empty((S, ld), dtype)]
+        eng.trace_device(ent["tables"][li], d[0], d[1], *ref, N=n, ld=ld, clip=True)
+        single.append(ref)
+        outs.append([eng.empty((S, ld, 3), dtype) for _ in range(3)] + [eng.empty((S, ld), dtype)])
+    eng.trace_device_batch(ent["tables"][:3], [r[0] for r in rays], [r[1] for r in rays],
+                           [o[0] for o in outs], [o[1] for o in outs], [o[2] for o in outs],
+                           [o[3] for o in outs], Ns=ns, ld=ld, clip=True)
+    eng.sync()
+    for n, a, b in zip(ns, single, outs):
+        for x, y in zip(a, b):
+            assert np.array_equal(x.download()[:, :n], y.download()[:, :n], equal_nan=True)
+    for group in single + outs:
+        for a in group:
+            a.free()
