@@ -15,6 +15,20 @@ ref = eng.trace(table, y0, u0, clip=True, direct=True)
 for kw in (dict(), dict(rpt=1), dict(rpt=2), dict(exact=True), dict(dtype=np.float32), dict(keep_last=True)):
     out = eng.trace(table, y0, u0, clip=True, **kw)
     print(kw, out[0].shape, flush=True)
+# side outputs, fused gather destinations, batched bundles
+d_y0, d_u0 = eng.to_device(y0), eng.to_device(u0)
+mask = eng.empty(((len(y0) + 31)//32,), np.uint32)
+acc = eng.empty((len(y0),))
+eng.trace_device(table, d_y0, d_u0, None, None, None, None, N=len(y0), clip=True, mask=mask, path_sum=acc)
+bufs = [eng.empty((len(y0) + 256, 3)) for _ in range(2)]
+eng.trace_gather(table, d_y0, d_u0, [b.ptr for b in bufs], 128, clip=True)
+S, ld = len(table), (len(y0) + 63)//64*64
+outs = [[eng.empty((S, ld, 3)) for _ in range(3)] + [eng.empty((S, ld))] for _ in range(2)]
+eng.trace_device_batch([table, ent["tables"][1]], [d_y0, d_y0], [d_u0, d_u0], [o[0] for o in outs],
+                       [o[1] for o in outs], [o[2] for o in outs], [o[3] for o in outs],
+                       Ns=[len(y0), 33000], ld=ld, clip=True)
+eng.sync()
+print("side outputs / gather / batch ok", flush=True)
 c = load_golden("cooke_asph_f07_clip")
 eng.trace(c["table"], c["y0"], c["u0"], clip=True)
 c = load_golden("tilted_clip1")
