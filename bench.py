@@ -267,7 +267,7 @@ def main():
     k_ms = statistics.mean(per_launch)
     alg_bytes = N*(6*w + 10*w*S)
     # DRAM traffic per launch: dram__bytes_read.sum + dram__bytes_write.sum of
-    # this kernel at this size from ncu (profiles/r1_v7_dram_bytes_full_size.csv:
+    # this kernel at this size from ncu (profiles/r1_v8_dram_bytes_full_size.csv:
     # 0.481 GB read + 9.536 GB written; the last ~64 MB of results are still
     # in L2 when the kernel ends).  Only valid for the default workload.
     traffic = 10_017_000_000 if (N == N_RAYS and not args.direct) else None
@@ -428,7 +428,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved/peak, "traffic": traffic,
                          "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum per launch, "
-                                           "profiles/r1_v7_dram_bytes_full_size.csv",
+                                           "profiles/r1_v8_dram_bytes_full_size.csv",
                          "peak_source": peak_src,
                          "kernel": "rtx::trace_kernel<double>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg_bytes},
