@@ -302,6 +302,16 @@ int rtx_aim_infinite(rtx_ctx *ctx, int dtype, int64_t N, const void *yp,
                      void *u0);
 
 /*
+ * Same for a finite conjugate (FiniteConjugate.aim, rayopt/conjugates.py:
+ * 137-166; plane object surface, non-telecentric pupil, filter=False): frame =
+ * {y[3] object point, u[3] = (0,0,z) - y, s[3], m[3]}, am = max |arctan2(p, z)|
+ * (the pupil half-angle Pupil.map scales with), z the pupil distance.
+ */
+int rtx_aim_finite(rtx_ctx *ctx, int dtype, int64_t N, const void *yp,
+                   int hex_rings, const double *frame, double am, double z,
+                   void *y0, void *u0);
+
+/*
  * Moments for GeometricTrace.refocus (rayopt/geometric_trace.py:82-99) on
  * DEVICE arrays of one surface: y = intercepts (N,3), inc = incidence
  * directions (N,3); u = inc_xy/inc_z (tanarcsin); rays with non-finite u are

@@ -51,6 +51,7 @@ SYMBOLS = {
     "rtx_moments": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp]),
     "rtx_selftest_math": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "rtx_aim_infinite": (_i, [_vp, _i, _i64, _vp, _i, _vp, C.c_double, _vp, _vp]),
+    "rtx_aim_finite": (_i, [_vp, _i, _i64, _vp, _i, _vp, C.c_double, C.c_double, _vp, _vp]),
     "rtx_focus_moments": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "rtx_ipc_export": (_i, [_vp, _vp, _vp]),
     "rtx_ipc_open": (_i, [_vp, _vp, _pp]),

@@ -305,6 +305,22 @@ class Engine:
                                         rings, ptr(frame), pmax, y0.ptr, u0.ptr))
         return y0, u0
 
+    def aim_finite_device(self, yo, z, p, radius, yp=None, nrays=None, dtype=np.float64):
+        """Launch rays of an aimed bundle from a FINITE object generated in HBM
+        (rtx_aim_finite; host restatement: rays.aim_finite).  Returns (y0, u0)."""
+        from .rays import finite_frame
+        frame = np.ascontiguousarray(np.concatenate(finite_frame(yo, z, radius)), np.float64)
+        am = float(np.fabs(np.arctan2(np.asarray(p, float), z)).max())
+        if yp is None:
+            rings = int(np.sqrt(nrays/3. - 1/12.) - 1/2.)
+            N = 1 + 3*rings*(rings + 1)
+        else:
+            rings, N = 0, yp.shape[0]
+        y0, u0 = self.empty((N, 3), dtype), self.empty((N, 3), dtype)
+        check(self.lib.rtx_aim_finite(self.ctx, _code(dtype), N, None if yp is None else yp.ptr,
+                                      rings, ptr(frame), am, float(z), y0.ptr, u0.ptr))
+        return y0, u0
+
     def aim_infinite_into(self, y_dst, u_dst, count, rings, frame, pmax, yp=None):
         """rtx_aim_infinite into existing device rows (DeviceArray views)"""
         frame = np.ascontiguousarray(frame, np.float64)

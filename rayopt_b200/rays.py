@@ -1,4 +1,5 @@
-"""Launch-ray generation for aimed bundles (host numpy).
+"""Launch-ray generation for aimed bundles (host numpy restatements; the device
+kernels rtx_aim_infinite / rtx_aim_finite follow them operation by operation).
 
 Restates, for the cases the benchmark workloads need, what the reference does
 upstream of the hot path:  ``InfiniteConjugate.aim`` with the rectilinear
@@ -72,4 +73,42 @@ def aim_infinite(yo, yp, z, p, angle):
     m /= np.sqrt(np.square(m).sum(-1))[..., None]
     y += yp[..., 0, None]*s + yp[..., 1, None]*m           # conjugates.py:252
     y += (-y[:, 2]/u[:, 2])[..., None]*u                   # plane object surface, :254
+    return y, u
+
+
+def finite_frame(yo, z, radius):
+    """Per-field constants of aim_finite: object point y (3,), chief direction
+    u = (0,0,z) - y (3,), normalised sagittal and meridional axes s, m (3,)."""
+    yo = np.atleast_2d(np.asarray(yo, float))
+    y = np.zeros((1, 3))
+    y[..., :2] = -yo*radius                                # conjugates.py:151
+    uz = np.array((0, 0, z), float)
+    u = uz - y                                             # conjugates.py:158
+    s = np.cross(u, uz)
+    if np.all(s == 0):
+        s = np.array([[1., 0, 0]])
+    m = np.cross(u, s)
+    s = s/np.sqrt(np.square(s).sum(-1))[..., None]
+    m = m/np.sqrt(np.square(m).sum(-1))[..., None]
+    return y[0], u[0], s[0], m[0]
+
+
+def aim_finite(yo, yp, z, p, radius):
+    """FiniteConjugate.aim (rayopt/conjugates.py:137-166) for a non-telecentric
+    pupil, a plane object surface and ``filter=False``: object point at
+    ``-yo*radius``, pupil coordinates mapped through the pupil half-angles
+    ``arctan2(p, z)`` (Pupil.map, rayopt/pupils.py:97-101), direction
+    ``normalize(u + z tan(yp_x) s + z tan(yp_y) m)``, flipped if z < 0."""
+    yp = np.atleast_2d(np.asarray(yp, float))
+    a = np.arctan2(np.asarray(p, float), z)                # conjugates.py:146
+    yp = yp*np.fabs(a).max()                               # pupils.py:100-101
+    yp = z*np.tan(yp)                                      # conjugates.py:149
+    y0, u0, s, m = finite_frame(yo, z, radius)
+    n = yp.shape[0]
+    y = np.broadcast_to(y0, (n, 3)).copy()
+    u = np.broadcast_to(u0, (n, 3)).copy()
+    u += yp[..., 0, None]*s + yp[..., 1, None]*m           # conjugates.py:161
+    u /= np.sqrt(np.square(u).sum(-1))[..., None]          # normalize, utils.py:97-98
+    if z < 0:
+        u *= -1
     return y, u

@@ -573,3 +573,23 @@ def test_batched_bundles_one_launch(eng, systems, dtype):
     for group in single + outs:
         for a in group:
             a.free()
+
+
+def test_device_ray_generation_finite(eng):
+    """rtx_aim_finite vs the host restatement of FiniteConjugate.aim (which is
+    bit-identical to the reference): to the last ulps of tan()"""
+    from rayopt_b200.rays import aim_finite, hexapolar
+    p = np.array(((-3., -2.5), (3., 2.5)))
+    for z in (50., -40.):
+        yp = disc(4001, 8)
+        hy, hu = aim_finite((.3, -.4), yp, z, p, 5.)
+        dy, du = eng.aim_finite_device((.3, -.4), z, p, 5., yp=eng.to_device(yp))
+        eng.sync()
+        assert np.array_equal(dy.download(), hy)
+        np.testing.assert_allclose(du.download(), hu, rtol=0, atol=4e-16)
+        rings, xy = hexapolar(3000)
+        hy, hu = aim_finite((0, .7), xy, z, p, 5.)
+        dy, du = eng.aim_finite_device((0, .7), z, p, 5., nrays=3000)
+        eng.sync()
+        np.testing.assert_allclose(du.download(), hu, rtol=0, atol=1e-15)
+        assert np.allclose(np.square(du.download()).sum(1), 1, rtol=0, atol=4e-16)

@@ -51,3 +51,23 @@ def test_aim_matches_reference_golden():
     y, u = aim_infinite((0, .7), disc(256, 0), c["meta"]["z"], c["meta"]["p"],
                         np.deg2rad(14))
     assert np.array_equal(y, c["y0"]) and np.array_equal(u, c["u0"])
+
+
+def test_aim_finite_restatement_vs_reference():
+    """rays.aim_finite == FiniteConjugate.aim (rayopt/conjugates.py:137-166)
+    bit for bit (live reference only)"""
+    import pytest
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    import warnings
+    warnings.simplefilter("ignore")
+    R = ref_shim.load()
+    from rayopt_b200.rays import aim_finite
+    fc = R.conjugates.FiniteConjugate(radius=5., pupil=dict(type="radius", radius=3., distance=50.))
+    a = np.array(((-3., -2.5), (3., 2.5)))
+    for z in (50., -40.):
+        for yo in ((0, .7), (0., 0.), (.3, -.4)):
+            y, u = fc.aim(np.array(yo), disc(500, 2), z=z, a=a.copy(), surface=None, filter=False)
+            hy, hu = aim_finite(yo, disc(500, 2), z, a, 5.)
+            assert np.array_equal(y, hy) and np.array_equal(u, hu)
