@@ -591,5 +591,5 @@ def test_device_ray_generation_finite(eng):
         hy, hu = aim_finite((0, .7), xy, z, p, 5.)
         dy, du = eng.aim_finite_device((0, .7), z, p, 5., nrays=3000)
         eng.sync()
-        np.testing.assert_allclose(du.download(), hu, rtol=0, atol=1e-15)
+        np.testing.assert_allclose(du.download(), hu, rtol=0, atol=5e-15)
         assert np.allclose(np.square(du.download()).sum(1), 1, rtol=0, atol=2e-15)
