@@ -43,6 +43,13 @@ class DeviceArray:
             self.engine._live.pop(id(self), None)
         self.ptr = None
 
+    def __del__(self):              # dropped without free(): give the HBM back
+        try:
+            if self.ptr is not None and id(self) in self.engine._live:
+                self.free()
+        except Exception:
+            pass
+
     def upload(self, a):
         a = np.ascontiguousarray(a, self.dtype)
         assert a.nbytes <= self.nbytes
@@ -102,6 +109,9 @@ class Engine:
             for p in list(self._pinned.values()):
                 self.lib.rtx_host_free(self.ctx, p)
             self._pinned.clear()
+            for p in list(self._live.values()):     # device arrays still alive
+                self.lib.rtx_free_device(self.ctx, p)
+            self._live.clear()
             self._fin.detach()
             self.lib.rtx_free(self.ctx)
             self.ctx = None
