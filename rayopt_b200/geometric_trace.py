@@ -192,6 +192,43 @@ class GeometricTrace(PropagateMixin):
         self.propagate()
 
 
+    # ---- ray launch helpers of the reference (rayopt/geometric_trace.py:185-229),
+    # for a `system` that offers rayopt's aiming interface (System.pupil / aim /
+    # aim_chief, rayopt/system.py:504-593); ray aiming stays host Python
+    def rays(self, yo, yp, wavelength, stop=None, filter=None, clip=False, weight=None, ref=0):
+        """aim pupil coordinates `yp` from field point `yo`, trace
+        (geometric_trace.py:195-202)"""
+        z, p = self.system.pupil(yo, l=wavelength, stop=stop)
+        y, u = self.system.aim(yo, yp, z, p, filter=(not clip) if filter is None else filter)
+        self.rays_given(y, u, wavelength, weight, ref)
+        self.propagate(clip=clip)
+
+    def rays_point(self, yo, wavelength=None, nrays=11, distribution="meridional", filter=None,
+                   stop=None, clip=False):
+        """a pupil distribution from one field point (geometric_trace.py:204-209)"""
+        from rayopt.utils import pupil_distribution        # the reference's own grids
+        ref, yp, weight = pupil_distribution(distribution, nrays)
+        self.rays(yo, yp, wavelength, filter=filter, stop=stop, clip=clip, weight=weight, ref=ref)
+
+    def rays_clipping(self, yo, wavelength=None, axis=1):
+        """chief and the two rim rays along `axis` (geometric_trace.py:211-215)"""
+        z, p = self.system.pupil(yo, l=wavelength, stop=-1)
+        yp = np.zeros((3, 2))
+        yp[1:, axis] = p[:, axis]/np.fabs(p).max()
+        self.rays(yo, yp, wavelength, stop=-1, filter=False)
+
+    def rays_paraxial(self, paraxial=None):
+        """the two paraxial rays as real rays (geometric_trace.py:185-193)"""
+        par = self.system.paraxial if paraxial is None else paraxial
+        y = np.zeros((2, 2))
+        u = np.zeros((2, 2))
+        y[:, par.axis] = par.y[0]
+        tan_u = np.asarray(par.u[0], float)
+        u[:, par.axis] = tan_u*(1/np.sqrt(1 + np.square(tan_u)))   # sinarctan, utils.py:60-72
+        self.rays_given(y, u)
+        self.propagate()
+
+
 def bind(reference_trace_class, engine=None, dtype=np.float64, exact=False):
     """Subclass of the reference's GeometricTrace with the hot path replaced.
 

@@ -349,3 +349,28 @@ def test_resident_rays_point_matches_reference():
     ref.rays_point((0, 1.), nrays=60, distribution="square", clip=False)
     got.rays_point((0, 1.), nrays=60, distribution="square", clip=False)
     assert np.array_equal(np.asarray(got.y), ref.y, equal_nan=True)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+def test_standalone_ray_launch_helpers_match_reference():
+    """GeometricTrace.rays / rays_point / rays_clipping / rays_paraxial of the
+    standalone class (geometric_trace.py:185-215 restated) on a reference
+    System give the reference's traces"""
+    warnings.simplefilter("ignore")
+    R = ref_shim.load()
+    s = R.System(**yaml.safe_load(systems_yaml.COOKE))
+    s.update()
+    s.paraxial.refocus()
+    s.paraxial.update_conjugates()
+    ref, got = R.GeometricTrace(s), GeometricTrace(s, engine=OracleEngine())
+    for fn, args, kw in (("rays_point", ((0, 1.),), dict(nrays=40, distribution="hexapolar", clip=True)),
+                         ("rays_point", ((0, .5),), dict(nrays=9, distribution="meridional")),
+                         ("rays_clipping", ((0, 1.),), {}),
+                         ("rays_paraxial", (), {}),
+                         ("rays", ((0, .7), np.array([[0, 0], [.5, .5], [-.3, .9]]), s.wavelengths[1]),
+                          dict(clip=True))):
+        getattr(ref, fn)(*args, **kw)
+        getattr(got, fn)(*args, **kw)
+        for k in "yuit":
+            assert np.array_equal(getattr(got, k), getattr(ref, k), equal_nan=True), (fn, k)
+        assert np.array_equal(got.n, ref.n) and got.ref == ref.ref
