@@ -217,6 +217,25 @@ class GeometricTrace(PropagateMixin):
         yp[1:, axis] = p[:, axis]/np.fabs(p).max()
         self.rays(yo, yp, wavelength, stop=-1, filter=False)
 
+    def rays_line(self, yo, wavelength=None, nrays=21, eps=1e-2):
+        """chief ray plus a meridional and a sagittal neighbour (pupil offset
+        `eps`) for `nrays` field points from the axis to `yo`
+        (geometric_trace.py:217-229); rows are grouped [chief | meridional |
+        sagittal]"""
+        s = self.system
+        fields = np.linspace(0, 1, nrays)[:, None]*np.atleast_2d(yo)
+        offsets = np.zeros((3, 2))
+        offsets[1, 1] = offsets[2, 0] = eps
+        y = np.empty((3, nrays, 3))
+        u = np.empty((3, nrays, 3))
+        z, p = s.pupil((0, 0), l=wavelength)
+        reach = np.fabs(p).max()
+        for k, f in enumerate(fields):
+            z = s.aim_chief(f, z, reach, l=wavelength)
+            y[:, k], u[:, k] = s.aim(f, offsets, z, p)
+        self.rays_given(y.reshape(-1, 3), u.reshape(-1, 3), wavelength)
+        self.propagate()
+
     def rays_paraxial(self, paraxial=None):
         """the two paraxial rays as real rays (geometric_trace.py:185-193)"""
         par = self.system.paraxial if paraxial is None else paraxial

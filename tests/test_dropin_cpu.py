@@ -366,6 +366,7 @@ def test_standalone_ray_launch_helpers_match_reference():
     for fn, args, kw in (("rays_point", ((0, 1.),), dict(nrays=40, distribution="hexapolar", clip=True)),
                          ("rays_point", ((0, .5),), dict(nrays=9, distribution="meridional")),
                          ("rays_clipping", ((0, 1.),), {}),
+                         ("rays_line", ((0, 1.),), dict(nrays=5)),
                          ("rays_paraxial", (), {}),
                          ("rays", ((0, .7), np.array([[0, 0], [.5, .5], [-.3, .9]]), s.wavelengths[1]),
                           dict(clip=True))):
