@@ -11,17 +11,28 @@ y,u,i,t stored).  Metric: ray-surface intersections per second.
 
   value     device-resident inputs and outputs, CUDA events on the launching
             stream around exactly K steps (max over ranks)
-  e2e       the same work through the host-buffer C-ABI call rtx_trace_host:
-            H2D of the launch rays and D2H of the whole trace inside the
-            timed region (pinned host buffers)
+  e2e       the same work through the call a user makes,
+            GeometricTrace.propagate() on host arrays -> rtx_trace_host: H2D of
+            the launch rays and D2H of the whole trace inside the timed region
+            (page-locked host buffers, NUMA-local to the GPU);
+            e2e.spot_consumer: the resident drop-in (what
+            bind(rayopt.GeometricTrace, resident=True) runs): rays up,
+            kernel, only y[-1] back -- what a spot-diagram consumer reads
   roofline  HBM: algorithmic bytes N*(6w + 10w*S) per launch / mean launch
             duration (CUDA events around every launch, separate pass)
-  cpu_baseline  the numpy oracle port of the reference path on the host cores,
-            bounded sample
+  cpu_baseline  the REFERENCE itself (oracle/_ref, staged by oracle/make_ref.py)
+            on all host cores, bounded sample; numpy port as fallback
+  headline  (N=1, when the HBM is free) the north-star point: zoom S=20,
+            1e8 rays, FP64, full trace resident, one launch
+  multi_gpu (N>1) C4: every rank traces 1.25e8 rays generated in HBM and the
+            SAME kernel stores y[-1] into the gather buffers of all ranks over
+            NVLink (rtx_trace_gather); C5: the 25 zoom bundles split by rays
+            so that every rank carries 25/N bundles' worth
+  parity_ok samples of the timed results checked against the oracle (asserted)
 
-`--impl reference` times the reference's CPU path (the numpy port in oracle/,
-the reference itself being pure Python that cannot travel to the GPU box) on
-all host cores, on a bounded sample of the same workload per step.
+`--impl reference` times the reference's own CPU path -- GeometricTrace.
+rays_given + propagate of quartiq/rayopt, ray-sharded over all host cores --
+on a bounded sample of the same workload per step (oracle/cpu_bench.py).
 """
 import argparse
 import json
@@ -41,9 +52,11 @@ METRIC = "ray-surface intersections/sec"
 UNIT = "ray-surfaces/s"
 SYSTEM = "double_gauss"
 FIELD_INDEX = 3            # field (0, 0.7) in tests/golden/systems.json
+FIELD = (0., .7)
 N_RAYS = 10_000_000        # per wavelength
 WORKLOAD = ("C2: Double-Gauss 12-surface, 1e7 rays x 3 wavelengths, FP64, "
             "clip=True, field (0,0.7), full trace (y,u,i,t) stored")
+CPU_RAYS_PER_PROC = 400_000
 
 
 def load_system(name):
@@ -129,44 +142,219 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_port(ent, n_per_proc, procs, repeat=1):
-    """numpy oracle port of the reference path, ray-sharded over `procs`
-    processes; returns (ray-surfaces/s, seconds, rays per wavelength)"""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import cpu_bench
-    return cpu_bench.run(ent, FIELD_INDEX, n_per_proc, procs, repeat)
+def cpu_reference(steps, warmup, rays_per_proc=CPU_RAYS_PER_PROC):
+    """The reference's CPU path on all host cores, in its own process
+    (oracle/cpu_bench.py: no fork out of a CUDA process, no inherited NUMA
+    binding).  Returns cpu_bench's dict."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "cpu_bench.py"), "--system", SYSTEM,
+           "--field", str(FIELD[0]), str(FIELD[1]), "--rays-per-proc", str(rays_per_proc),
+           "--steps", str(steps), "--warmup", str(warmup)]
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def cpu_sample_text(r):
+    return ("%d rays x %d wavelengths x %d surfaces per step (of 1e7 per wavelength): %d "
+            "processes x %d rays each, GeometricTrace.rays_given + propagate(clip=True), "
+            "%.1f s per step" % (r["rays_per_step_and_wavelength"], r["wavelengths"],
+                                 r["surfaces"], r["cores"], r["rays_per_proc"],
+                                 statistics.mean(r["seconds"])))
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (numpy port) on all cores"""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: quartiq/rayopt's own GeometricTrace on all cores"""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    ent = load_system(SYSTEM)
-    cores = os.cpu_count() or 1
-    n_per_proc = 50000
-    for _ in range(args.warmup):
-        cpu_port(ent, 2000, cores)
-    tot_rs, dt = 0.0, 0.0
-    for _ in range(args.steps):
-        rate, secs, n = cpu_port(ent, n_per_proc, cores)   # secs: the trace only
-        tot_rs += n*3*ent["S"]
-        dt += secs
-    value = tot_rs/dt
-    sample = "%d rays x 3 wavelengths x %d surfaces per step (of 1e7), %d processes" % (
-        n_per_proc*cores, ent["S"], cores)
+    r = cpu_reference(args.steps, max(args.warmup, 1))
+    sample = cpu_sample_text(r)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt/args.steps*1e3, "higher_is_better": True,
+        "ms_per_step": statistics.mean(r["seconds"])*1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"],
+                         "kind": r["kind"], "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def rel_err(a, b):
+    with np.errstate(invalid="ignore"):
+        return float(np.nanmax(np.abs(a - b)/np.maximum(np.abs(b), 1.0)))
+
+
+def check_sample(got, want, what, tol=1e-10):
+    """parity of a sample of timed results: identical NaN mask, rel err <= tol"""
+    ok = bool(np.array_equal(np.isnan(got), np.isnan(want)))
+    err = rel_err(got, want) if ok else float("inf")
+    return {"what": what, "nan_mask_equal": ok, "max_rel_err": err, "ok": ok and err <= tol}
+
+
+# --------------------------------------------------------------------------
+def leg_headline(eng, exact):
+    """north-star point on one GPU: zoom S=20, ~1e8 rays (hexapolar grid
+    generated in HBM), FP64, full trace resident, ONE launch per trace"""
+    from rayopt_b200.rays import aim_infinite, hexapolar_xy
+    ent = load_system("zoom")
+    S, table, aim = ent["S"], ent["tables"][0], ent["aim"][0][FIELD_INDEX]
+    rings = int(np.sqrt(1e8/3. - 1/12.) - 1/2.)
+    N = 1 + 3*rings*(rings + 1)
+    ld = (N + 63)//64*64
+    need = N*48 + S*ld*80
+    free = eng.free_bytes()
+    if free < need + (2 << 30):
+        return {"skipped": "needs %.1f GB of HBM, %.1f GB free" % (need/1e9, free/1e9)}
+    y0, u0 = eng.aim_infinite_device(aim["field"], aim["z"], aim["p"], ent["object_angle"],
+                                     nrays=10**8)
+    out = [eng.empty((S, ld, 3)) for _ in range(3)] + [eng.empty((S, ld))]
+    ms = []
+    for _ in range(4):
+        eng.trace_device(table, y0, u0, *out, N=N, ld=ld, clip=True, exact=exact)
+        ms.append(eng.last_kernel_ms())
+    k_ms = statistics.median(ms[1:])
+    idx = np.unique(np.r_[0, np.random.default_rng(5).integers(1, N, 1500)])
+    hy, hu = aim_infinite(aim["field"], hexapolar_xy(idx, rings), aim["z"], aim["p"],
+                          ent["object_angle"])
+    import np_oracle
+    want = np_oracle.trace(table, hy, hu, clip=True)
+    got = np.stack([np.stack([eng.download_rays(out[0].rows(j), idx) for j in range(S)]),
+                    np.stack([eng.download_rays(out[1].rows(j), idx) for j in range(S)])])
+    par = check_sample(got, np.stack([want[0], want[1]]), "headline y,u sample of %d rays" % len(idx))
+    for a in [y0, u0] + out:
+        a.free()
+    alg = N*(48 + 80*S)
+    peak, _ = peaks()
+    return {"workload": "zoom S=20, %d rays (hexapolar grid generated in HBM), FP64, clip, full "
+                        "trace resident, one launch" % N,
+            "kernel_ms": k_ms, "all_ms": ms, "ray_surfaces_per_s": N*S/k_ms*1e3,
+            "achieved_GBps": alg/k_ms/1e6, "frac": alg/k_ms/1e6/peak,
+            "algorithmic_bytes": alg, "parity": par}
+
+
+def leg_c4(eng, dist, torch, exact, n_local=125_000_000):
+    """C4: 1.25e8 rays per rank generated in HBM, trace + all-gather of y[-1]
+    in one kernel per rank (TMA bulk stores into the IPC-mapped gather buffers
+    of ALL ranks over NVLink)"""
+    from rayopt_b200.rays import aim_infinite, hexapolar_xy
+    from rayopt_b200.sharding import PeerGather
+    import np_oracle
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ent = load_system(SYSTEM)
+    S, table = ent["S"], ent["tables"][0]
+    n_local = n_local//64*64
+    fields = [0, 3, 1, 2, 4, 3, 1, 2]                  # a field point per rank
+    aim = ent["aim"][0][fields[rank % 8]]
+    rings = int(np.sqrt((n_local + 4096)/3. - 1/12.) - 1/2.) + 1
+    y0, u0 = eng.aim_infinite_device(aim["field"], aim["z"], aim["p"], ent["object_angle"],
+                                     rings=rings)
+    assert y0.shape[0] >= n_local
+    pg = PeerGather(eng, dist, n_local*world)
+
+    def run():
+        eng.trace_gather(table, y0, u0, pg.ptrs, pg.b[rank], N=n_local, clip=True, exact=exact)
+        eng.sync()
+        dist.barrier()
+    run()                                               # warm-up: IPC mappings, peer access
+    kms, wall = [], []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        run()
+        wall.append(time.perf_counter() - t0)
+        kms.append(eng.last_kernel_ms())
+    t = torch.tensor([statistics.median(kms), statistics.median(wall)*1e3], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    kms_max, wall_max = (float(x) for x in t)
+    # a sample of the NEXT rank's segment as it arrived in THIS rank's buffer
+    peer = (rank + 1) % world
+    aim_p = ent["aim"][0][fields[peer % 8]]
+    idx = np.unique(np.r_[0, np.random.default_rng(rank).integers(1, n_local, 400)])
+    hy, hu = aim_infinite(aim_p["field"], hexapolar_xy(idx, rings), aim_p["z"], aim_p["p"],
+                          ent["object_angle"])
+    want = np_oracle.trace(table, hy, hu, clip=True)[0][-1]
+    got = eng.download_rays(pg.buf, pg.b[peer] + idx)
+    par = check_sample(got, want, "peer segment")
+    ok = torch.tensor([1.0 if par["ok"] else 0.0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    pg.close()
+    y0.free()
+    u0.free()
+    return {"workload": "C4: Double-Gauss, %d rays per rank (%.3g total) generated in HBM, FP64, "
+                        "trace + gather of y[-1] to all %d ranks in one kernel per rank"
+                        % (n_local, n_local*world, world),
+            "kernel_ms_max_over_ranks": kms_max, "wall_ms_max_over_ranks": wall_max,
+            "ray_surfaces_per_s": world*n_local*S/(kms_max*1e-3),
+            "nvlink_bytes_sent_per_rank": (world - 1)*n_local*24,
+            "nvlink_GBps_per_rank": (world - 1)*n_local*24/(kms_max*1e-3)/1e9,
+            "peer_segment_parity_ok": bool(ok.item() == 1.0), "parity_this_rank": par}
+
+
+def leg_c5(eng, dist, torch, exact, NR=10_000_000):
+    """C5: zoom S=20, 5 fields x 5 wavelengths x ~1e7 rays.  The 25 bundles
+    form one ray space split evenly over the ranks (by rays: a rank carries
+    25/world bundles' worth -- whole bundles plus at most two partial ones);
+    launch rays generated in HBM, full trace (y,u,i,t) stored."""
+    import np_oracle
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ent = load_system("zoom")
+    S = ent["S"]
+    field_idx = [0, 1, 2, 4, 5]                        # fields 0, .25, .5, .75, 1
+    bundles = [(fi, li) for fi in field_idx for li in range(5)]
+    rings = int(np.sqrt(NR/3. - 1/12.) - 1/2.)
+    N = 1 + 3*rings*(rings + 1)
+    total = len(bundles)*N
+    g0, g1 = rank*total//world//64*64, ((rank + 1)*total//world//64*64 if rank + 1 < world else total)
+    segs = []                                           # (bundle, lo, hi) owned by this rank
+    for b in range(len(bundles)):
+        lo, hi = max(g0, b*N) - b*N, min(g1, (b + 1)*N) - b*N
+        if hi > lo:
+            segs.append((b, lo, hi))
+    work = []
+    for b, lo, hi in segs:
+        fi, li = bundles[b]
+        aim = ent["aim"][li][fi]
+        y0, u0 = eng.aim_infinite_device(aim["field"], aim["z"], aim["p"], ent["object_angle"],
+                                         nrays=NR)
+        n = hi - lo
+        ld = (n + 63)//64*64
+        out = [eng.empty((S, ld, 3)) for _ in range(3)] + [eng.empty((S, ld))]
+        work.append((ent["tables"][li], y0.rows(lo, hi), u0.rows(lo, hi), out, n, ld, y0, u0))
+
+    def step():
+        for table, y0, u0, out, n, ld, _, _ in work:
+            eng.trace_device(table, y0, u0, *out, N=n, ld=ld, clip=True, exact=exact)
+    step()
+    eng.sync()
+    dist.barrier()
+    reps = 3
+    eng.timer_start()
+    for _ in range(reps):
+        step()
+    ms = eng.timer_stop()/reps
+    t = torch.tensor([ms], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    worst = float(t.item())
+    table, y0, u0, out, n, ld, _, _ = work[-1]
+    idx = np.arange(0, n, max(1, n//1500))
+    hy, hu = eng.download_rays(y0, idx), eng.download_rays(u0, idx)
+    want = np_oracle.trace(table, hy, hu, clip=True)
+    got = np.stack([eng.download_rays(out[0].rows(j), idx) for j in range(S)])
+    par = check_sample(got, want[0], "last segment y")
+    ok = torch.tensor([1.0 if par["ok"] else 0.0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    mine = sum(w[4] for w in work)
+    for w in work:
+        for a in w[3] + [w[6], w[7]]:
+            a.free()
+    return {"workload": "C5: zoom S=20, 5 fields x 5 wavelengths x %d rays (25 bundles, split by "
+                        "rays: %.3f bundles per rank), FP64, full trace stored" % (N, 25/world),
+            "rays_this_rank": mine, "segments_this_rank": len(work),
+            "step_ms_this_rank": ms, "step_ms_max_over_ranks": worst,
+            "ray_surfaces_per_s": total*S/(worst*1e-3),
+            "per_gpu_GBps": mine*(48 + 80*S)/(ms*1e-3)/1e9,
+            "parity_ok": bool(ok.item() == 1.0), "parity_this_rank": par}
 
 
 def main():
@@ -181,6 +369,8 @@ def main():
     ap.add_argument("--rpt", type=int, default=0, help="rays per thread (0: library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-headline", action="store_true")
+    ap.add_argument("--no-multi", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -188,7 +378,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
+    dist = torch = None
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -196,19 +386,33 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from rayopt_b200.engine import Engine
-    eng = Engine(local)
+    # this process and its page-locked buffers live on the GPU's NUMA node
+    eng = Engine(local, numa=True)
     ent = load_system(SYSTEM)
     S, nl, N = ent["S"], len(ent["tables"]), args.rays
     ld = ((N + 63)//64)*64
     w = 8
+    exact = bool(args.exact)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))   # the checker of the timed results
+    import np_oracle
+    checks = []
+
+    def maxr(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([float(x)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- device-resident workload: 3 bundles, 3 full result sets ----------
     host_rays = []
     dev = []
     for li in range(nl):
         y0, u0 = make_rays(ent, li, N, seed=1000*rank + li)
-        host_rays.append((y0, u0))
-        d = {"y0": eng.to_device(y0), "u0": eng.to_device(u0),
+        py, pu = eng.pinned_empty(y0.shape), eng.pinned_empty(u0.shape)
+        py[:], pu[:] = y0, u0
+        host_rays.append((py, pu))
+        d = {"y0": eng.to_device(py), "u0": eng.to_device(pu),
              "Y": eng.empty((S, ld, 3)), "U": eng.empty((S, ld, 3)),
              "I": eng.empty((S, ld, 3)), "T": eng.empty((S, ld))}
         dev.append(d)
@@ -217,14 +421,13 @@ def main():
         for li in range(nl):
             d = dev[li]
             eng.trace_device(ent["tables"][li], d["y0"], d["u0"], d["Y"], d["U"], d["I"],
-                             d["T"], N=N, ld=ld, clip=True, exact=bool(args.exact),
+                             d["T"], N=N, ld=ld, clip=True, exact=exact,
                              direct=bool(args.direct), rpt=args.rpt)
 
     def barrier():
         eng.sync()
         if dist is not None:
             dist.barrier()
-            import torch
             torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -247,11 +450,7 @@ def main():
         step()
     barrier()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = maxr(ms)
     ms_per_step = ms/args.steps
     value = world*nl*N*S/(ms_per_step*1e-3)
 
@@ -261,24 +460,24 @@ def main():
         for li in range(nl):
             d = dev[li]
             eng.trace_device(ent["tables"][li], d["y0"], d["u0"], d["Y"], d["U"], d["I"],
-                             d["T"], N=N, ld=ld, clip=True, exact=bool(args.exact),
+                             d["T"], N=N, ld=ld, clip=True, exact=exact,
                              direct=bool(args.direct), rpt=args.rpt)
             per_launch.append(eng.last_kernel_ms())
     k_ms = statistics.mean(per_launch)
     alg_bytes = N*(6*w + 10*w*S)
-    # DRAM traffic per launch: dram__bytes_read.sum + dram__bytes_write.sum of
-    # this kernel at this size from ncu (profiles/r1_v8_dram_bytes_full_size.csv:
-    # 0.481 GB read + 9.536 GB written; the last ~64 MB of results are still
-    # in L2 when the kernel ends).  Only valid for the default workload.
-    traffic = 10_017_000_000 if (N == N_RAYS and not args.direct) else None
     achieved = alg_bytes/(k_ms*1e-3)/1e9
     peak, peak_src = peaks()
+    # DRAM traffic per launch is NOT measurable from inside the process (it
+    # needs ncu): the number below is carried over from the committed ncu
+    # capture of this kernel at this size and labelled as such
+    traffic = 10_017_000_000 if (N == N_RAYS and not args.direct) else None
 
-    # samples of the timed results, checked against the oracle in the
-    # cpu_baseline leg below (the only place bench.py touches oracle/)
+    # ---- parity of the timed device-resident results (sample vs the oracle)
     idx = np.arange(0, N, max(1, N//2000))[:2000]
-    got_dev = np.stack([dev[0]["Y"].rows(j).download()[0][idx] for j in range(S)])
-
+    want0 = np_oracle.trace(ent["tables"][0], host_rays[0][0][idx], host_rays[0][1][idx], clip=True)
+    for k, j in (("Y", 0), ("U", 1), ("I", 2)):
+        got = np.stack([eng.download_rays(dev[0][k].rows(s), idx) for s in range(S)])
+        checks.append(check_sample(got, want0[j], "device-resident %s (bundle 0)" % k.lower()))
     for d in dev:
         for a in d.values():
             a.free()
@@ -290,41 +489,37 @@ def main():
     # one buffer (i[j] == u[j-1] bit for bit) and moves 56 B per ray-surface;
     # "full_copy" is the same through rtx_trace_host with all four arrays
     # (80 B per ray-surface).
+    def timed(fn, steps):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        barrier()
+        return maxr(time.perf_counter() - t0)
+
     e2e = None
-    got_e2e = None
     if not args.no_e2e:
-        from rayopt_b200 import GeometricTrace, PackedSystem
+        from rayopt_b200 import GeometricTrace, PackedSystem, ResidentTrace
         ps = PackedSystem(ent["wavelengths"], ent["tables"], [n[0] for n in ent["n"]])
         # one trace object (7.5 GB of page-locked result arrays), propagated
         # once per wavelength and step: the launch rays of bundle 0, the
         # surface table of each wavelength
-        g = GeometricTrace(ps, engine=eng, exact=bool(args.exact))
+        g = GeometricTrace(ps, engine=eng, exact=exact)
         g.rays_given(host_rays[0][0], host_rays[0][1], l=ent["wavelengths"][0])
 
         def e2e_step():
             for l in ent["wavelengths"]:
                 g.l = l
                 g.propagate(clip=True)
-
-        def timed(fn, steps):
-            fn()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(steps):
-                fn()
-            barrier()
-            dt = time.perf_counter() - t0
-            if dist is not None:
-                import torch
-                t = torch.tensor([dt], device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dt = float(t.item())
-            return dt
         e2e_steps = max(1, min(args.steps, 3))
         dt = timed(e2e_step, e2e_steps)
-        # samples of what came back to the host (last wavelength traced)
-        got_e2e = (g.y[1:, idx].copy(), g.i[1:, idx].copy(),
-                   bool(np.array_equal(g.i[2:, idx], g.u[1:-1, idx], equal_nan=True)))
+        # what came back to the host (last wavelength traced)
+        wl = np_oracle.trace(ent["tables"][nl - 1], host_rays[0][0][idx], host_rays[0][1][idx],
+                             clip=True)
+        checks.append(check_sample(g.y[1:, idx], wl[0], "e2e host arrays y"))
+        checks.append(check_sample(g.i[1:, idx], wl[2], "e2e host arrays i (view of u)"))
+        checks.append(check_sample(g.t[1:, idx], wl[3], "e2e host arrays t"))
         e2e = {"value": world*nl*N*S*e2e_steps/dt, "unit": UNIT,
                "h2d_bytes_per_step": nl*N*6*w, "d2h_bytes_per_step": nl*N*S*7*w,
                "steps": e2e_steps, "ms_per_step": dt/e2e_steps*1e3,
@@ -333,111 +528,104 @@ def main():
         del g
         import gc
         gc.collect()
+
+        # ---- spot-diagram consumer (rayopt/analysis.py:269-280) on the resident
+        # drop-in -- the class bind(rayopt.GeometricTrace, resident=True) puts in
+        # front of the reference: rays_given (H2D), propagate (one launch, trace
+        # stays in HBM), y[-1] (the only D2H)
+        r = ResidentTrace(ps, engine=eng, exact=exact)
+        spots = [None]*nl
+
+        def spot_step():
+            for li, l in enumerate(ent["wavelengths"]):
+                r.rays_given(host_rays[li][0], host_rays[li][1], l=l)
+                r.propagate(clip=True)
+                spots[li] = r.y[-1]
+        ssteps = max(1, min(args.steps, 5))
+        dt = timed(spot_step, ssteps)
+        wl = np_oracle.trace(ent["tables"][nl - 1], host_rays[nl - 1][0][idx],
+                             host_rays[nl - 1][1][idx], clip=True)
+        checks.append(check_sample(spots[nl - 1][idx], wl[0][-1], "resident spot y[-1]"))
+        e2e["spot_consumer"] = {
+            "value": world*nl*N*S*ssteps/dt, "unit": UNIT, "ms_per_step": dt/ssteps*1e3,
+            "h2d_bytes_per_step": nl*N*6*w, "d2h_bytes_per_step": nl*N*3*w,
+            "api": "ResidentTrace (the mixin behind bind(rayopt.GeometricTrace, resident=True)): "
+                   "rays_given + propagate(clip=True) + y[-1]; the trace stays in HBM"}
+        r.free()
+        del r, spots
+        gc.collect()
+
     if not args.no_e2e and world == 1:
         # all four arrays through the C ABI
         out = {"y": eng.pinned_empty((S, N, 3)), "u": eng.pinned_empty((S, N, 3)),
                "i": eng.pinned_empty((S, N, 3)), "t": eng.pinned_empty((S, N))}
-        pin = []
-        for y0, u0 in host_rays:
-            py, pu = eng.pinned_empty(y0.shape), eng.pinned_empty(u0.shape)
-            py[:], pu[:] = y0, u0
-            pin.append((py, pu))
 
         def full_step():
             for li in range(nl):
-                eng.trace(ent["tables"][li], pin[li][0], pin[li][1], clip=True, out=out,
-                          exact=bool(args.exact), rpt=args.rpt)
+                eng.trace(ent["tables"][li], host_rays[li][0], host_rays[li][1], clip=True,
+                          out=out, exact=exact, rpt=args.rpt)
         fsteps = max(1, min(args.steps, 2))
         dt = timed(full_step, fsteps)
         e2e["full_copy"] = {"value": world*nl*N*S*fsteps/dt, "ms_per_step": dt/fsteps*1e3,
                             "d2h_bytes_per_step": nl*N*S*10*w,
                             "api": "rtx_trace_host with y,u,i,t host outputs"}
+        del out
 
-    # ---- e2e for a spot-diagram consumer (rayopt/analysis.py:269-280): the
-    # trace stays in HBM (rayopt_b200.ResidentTrace semantics), per wavelength
-    # the launch rays go up and only y[-1] comes back
-    if not args.no_e2e and world == 1:
-        from rayopt_b200._lib import check, ptr
-        d_in = (eng.empty((N, 3)), eng.empty((N, 3)))
-        d_full = {"Y": eng.empty((S, ld, 3)), "U": eng.empty((S, ld, 3)),
-                  "I": eng.empty((S, ld, 3)), "T": eng.empty((S, ld))}
-        h_spot = eng.pinned_empty((N, 3))
+    # ---- the multi-GPU design: fused trace + NVLink gather (C4), C5 by rays
+    multi = None
+    if world > 1 and not args.no_multi:
+        multi = {"c4": leg_c4(eng, dist, torch, exact), "c5": leg_c5(eng, dist, torch, exact)}
+        checks.append({"what": "C4 peer segments (all ranks)", "ok": multi["c4"]["peer_segment_parity_ok"]})
+        checks.append({"what": "C5 samples (all ranks)", "ok": multi["c5"]["parity_ok"]})
 
-        def spot_step():
-            for li in range(nl):
-                check(eng.lib.rtx_memcpy_h2d(eng.ctx, d_in[0].ptr, ptr(pin[li][0]), pin[li][0].nbytes))
-                check(eng.lib.rtx_memcpy_h2d(eng.ctx, d_in[1].ptr, ptr(pin[li][1]), pin[li][1].nbytes))
-                eng.trace_device(ent["tables"][li], d_in[0], d_in[1], d_full["Y"], d_full["U"],
-                                 d_full["I"], d_full["T"], N=N, ld=ld, clip=True,
-                                 exact=bool(args.exact))
-                check(eng.lib.rtx_memcpy_d2h(eng.ctx, ptr(h_spot), d_full["Y"].rows(S - 1).ptr,
-                                             h_spot.nbytes))
-            eng.sync()
-        ssteps = max(1, min(args.steps, 5))
-        dt = timed(spot_step, ssteps)
-        e2e["spot_consumer"] = {"value": nl*N*S*ssteps/dt, "ms_per_step": dt/ssteps*1e3,
-                                "h2d_bytes_per_step": nl*N*6*w, "d2h_bytes_per_step": nl*N*3*w,
-                                "api": "device-resident full trace (ResidentTrace semantics): rays "
-                                       "up, kernel, only y[-1] back"}
-        for a in list(d_in) + list(d_full.values()):
-            a.free()
+    # ---- north-star point, driver-run when the GPU's memory allows ---------
+    headline = None
+    if world == 1 and not args.no_headline and N == N_RAYS:
+        headline = leg_headline(eng, exact)
+        if "parity" in headline:
+            checks.append(headline["parity"])
 
-    # ---- CPU baseline: numpy port of the reference path ------------------
-    # (also the checker of the timed GPU results: same rays, same tables)
+    # ---- CPU baseline: the reference itself on the host cores ---------------
     cpu = None
-    parity = None
-    if rank == 0 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        n_per_proc = 50000
-        rate, secs, n = cpu_port(ent, n_per_proc, cores, repeat=2)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d rays x 3 wavelengths x %d surfaces (of 1e7), %d processes, "
-                         "%.1f s" % (n, S, cores, secs)}
-        import np_oracle
+    node = eng.numa_node
+    eng.numa_bind(False)              # the CPU leg may use every core again
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_reference(steps=1, warmup=1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+               "sample": cpu_sample_text(r)}
 
-        def rel(a, b):
-            return float(np.nanmax(np.abs(a - b)/np.maximum(np.abs(b), 1.0)))
-        want = np_oracle.trace(ent["tables"][0], host_rays[0][0][idx], host_rays[0][1][idx],
-                               clip=True)
-        parity = {"sample_rays": len(idx),
-                  "device_resident": {
-                      "nan_mask_equal": bool(np.array_equal(np.isnan(got_dev), np.isnan(want[0]))),
-                      "max_rel_err_y": rel(got_dev, want[0])}}
-        if got_e2e is not None:
-            wl = np_oracle.trace(ent["tables"][nl - 1], host_rays[0][0][idx],
-                                 host_rays[0][1][idx], clip=True)
-            parity["e2e_host_arrays"] = {
-                "nan_mask_equal": bool(np.array_equal(np.isnan(got_e2e[0]), np.isnan(wl[0])) and
-                                       np.array_equal(np.isnan(got_e2e[1]), np.isnan(wl[2]))),
-                "max_rel_err_y": rel(got_e2e[0], wl[0]), "max_rel_err_i": rel(got_e2e[1], wl[2]),
-                "i_is_view_of_u": got_e2e[2]}
-
+    parity_ok = all(c["ok"] for c in checks)
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64", "data": "synthetic", "parity_ok": parity_ok,
             "config": {"workload": WORKLOAD, "rays_per_wavelength": N, "surfaces": S,
                        "wavelengths": nl, "parallelism": "rays sharded x%d" % world,
-                       "arithmetic": "exact" if args.exact else "fast",
+                       "arithmetic": "exact" if exact else "fast",
                        "stores": "direct" if args.direct else "tma-bulk",
                        "kernel_config": "rpt=%s store=%s warps=%s nbuf=%s (0/unset: library default rpt 2, per-CTA TMA bulk stores, 16 warps, 1 staging buffer)" % (args.rpt, os.environ.get("RTX_STORE", "-"), os.environ.get("RTX_WARPS", "-"), os.environ.get("RTX_NBUF", "-")),
+                       "numa_node": node,
                        "l2": "outputs %.1f GB per launch >> 126 MB L2 (no flush needed)"
                              % (alg_bytes/1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved/peak, "traffic": traffic,
-                         "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum per launch, "
-                                           "profiles/r1_v8_dram_bytes_full_size.csv",
+                         "traffic_source": "from profile, not measured in this run: ncu "
+                                           "dram__bytes_read.sum+dram__bytes_write.sum per launch of "
+                                           "this kernel at this size, profiles/r1_v8_dram_bytes_full_size.csv",
                          "peak_source": peak_src,
                          "kernel": "rtx::trace_kernel<double>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks, "parity_check": parity,
+            "clocks": clocks, "headline": headline, "multi_gpu": multi,
+            "parity_checks": checks,
         }))
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
     eng.close()
+    assert parity_ok, [c for c in checks if not c["ok"]]
 
 
 if __name__ == "__main__":

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define RTX_ABI_VERSION 1
+#define RTX_ABI_VERSION 2
 
 /* maximum number of even-asphere coefficients per surface (Spheroid.aspherics,
  * elements.py:422-424).  Longer lists are rejected with RTX_E_UNSUPPORTED. */
@@ -77,7 +77,6 @@ extern "C" {
 #define RTX_E_BADARG       -1
 #define RTX_E_UNSUPPORTED  -2
 #define RTX_E_NOMEM        -3
-#define RTX_E_NCCL         -4
 
 /*
  * One traced surface for one wavelength: everything System.propagate
@@ -135,10 +134,23 @@ int rtx_device_info(rtx_ctx *ctx, int *sm_count, size_t *free_bytes,
 int rtx_malloc(rtx_ctx *ctx, size_t bytes, void **dptr);
 int rtx_free_device(rtx_ctx *ctx, void *dptr);
 int rtx_host_alloc(rtx_ctx *ctx, size_t bytes, void **hptr); /* pinned */
+/* ctx may be NULL (page-locked memory may outlive the context that made it) */
 int rtx_host_free(rtx_ctx *ctx, void *hptr);
+/*
+ * NUMA placement of the calling thread (one process per GPU): enable = 1 pins
+ * the thread to the CPUs of the NUMA node this context's GPU hangs off
+ * (/sys/bus/pci/devices/<bus id>/numa_node) and makes that node the preferred
+ * one for its allocations, so that page-locked buffers allocated afterwards
+ * (rtx_host_alloc, the library's own bounce buffers) are local to the GPU's
+ * PCIe root; enable = 0 restores the affinity and policy saved by the last
+ * bind.  *node (may be NULL) receives the node, -1 when the platform does not
+ * report one (nothing is changed then).
+ */
+int rtx_numa_bind(rtx_ctx *ctx, int enable, int *node);
 /* asynchronous on the context stream; rtx_sync() to complete */
 int rtx_memcpy_h2d(rtx_ctx *ctx, void *dst, const void *src, size_t bytes);
 int rtx_memcpy_d2h(rtx_ctx *ctx, void *dst, const void *src, size_t bytes);
+int rtx_memcpy_d2d(rtx_ctx *ctx, void *dst, const void *src, size_t bytes);
 /* strided D2H: `height` rows of `width` bytes */
 int rtx_memcpy2d_d2h(rtx_ctx *ctx, void *dst, size_t dpitch, const void *src,
                      size_t spitch, size_t width, size_t height);
@@ -249,15 +261,21 @@ int rtx_ipc_close(rtx_ctx *ctx, void *dptr);
  * arrays of `dtype` that are local or peer-GPU memory (rtx_ipc_open) -- at ray
  * offset dst_offset: the all-gather of GeometricTrace.y[-1] is done by the
  * trace kernel's own TMA bulk stores over NVLink instead of a separate
- * collective.  dst_offset must be a multiple of 64 rays and every buffer
- * must hold dst_offset + N rounded up to 64 rays (whole 64-ray groups are
- * written).  Asynchronous on the context stream; after rtx_sync on every
- * rank and a cross-rank barrier all buffers hold the full spot.
+ * collective.  dst_i (may be NULL) is a second set of npeers buffers that
+ * receive the last surface's INCIDENCE directions i[-1] the same way (the
+ * through-focus spots of rayopt/analysis.py:274-280 read y[-1] and i[-1]).
+ * Bulk stores need dst_offset to be a multiple of 64 rays and write whole
+ * 64-ray groups: with N a multiple of 64 exactly rays dst_offset ..
+ * dst_offset + N - 1 are written; for any other N (or a misaligned offset /
+ * buffer) the library falls back to per-ray stores that touch exactly N rays,
+ * so a shard can never spill into its neighbour's range.  Asynchronous on
+ * the context stream; after rtx_sync on every rank and a cross-rank barrier
+ * all buffers hold the full spot.
  */
 int rtx_trace_gather(rtx_ctx *ctx, const rtx_surface *surf, int S,
                      const double *rot0, int dtype, int64_t N, const void *y0,
                      const void *u0, int clip, int npeers, void *const *dst,
-                     int64_t dst_offset, unsigned flags);
+                     void *const *dst_i, int64_t dst_offset, unsigned flags);
 
 /* ---- self-test --------------------------------------------------------- */
 /*

@@ -123,7 +123,7 @@ def intercept(rec, y, u):
         uu = 1.
         yy = np.square(y).sum(1)
     else:
-        kk = np.array([(1, 1, 1 + k)])                    # :489
+        kk = np.array([(1, 1, 1 + k)], y.dtype)           # :489 (float64 in the reference)
         uy = (u*y*kk).sum(1)
         uu = (np.square(u)*kk).sum(1)
         yy = (np.square(y)*kk).sum(1)
@@ -176,8 +176,11 @@ def propagate_surface(rec, y0, u0, do_clip):
 def trace(table, y0, u0, clip=False, rot0=None, dtype=np.float64):
     """GeometricTrace.propagate + System.propagate, geometric_trace.py:72-80,
     system.py:459-464.  Returns Y,U,I (S,N,3) and T (S,N) in `dtype`
-    arithmetic (float64 is the reference; float32 is only a convenience
-    for error budgeting of the FP32 engine)."""
+    arithmetic.  float64 is the reference.  float32 evaluates the SAME
+    expressions entirely in float32 (the table scalars enter as Python floats,
+    weak under NEP 50, so nothing is promoted): the error budget of "the
+    reference's formulas in single precision" that the FP32 engine is held
+    against in tests/test_gpu_parity.py."""
     dtype = np.dtype(dtype)
     y = np.array(y0, dtype)
     u = np.array(u0, dtype)
@@ -186,8 +189,6 @@ def trace(table, y0, u0, clip=False, rot0=None, dtype=np.float64):
     U = np.empty_like(Y)
     I = np.empty_like(Y)
     T = np.empty((S, N), dtype)
-    if dtype != np.float64:
-        table = _cast_table(table, dtype)
     with np.errstate(all="ignore"):
         if rot0 is not None:
             r = np.asarray(rot0, dtype).reshape(3, 3)
@@ -204,13 +205,6 @@ def trace(table, y0, u0, clip=False, rot0=None, dtype=np.float64):
             if rotated:
                 y, u = np.dot(y, r), np.dot(u, r)         # system.py:464
     return Y, U, I, T
-
-
-def _cast_table(table, dtype):
-    """float32 view of the scalars (float32 oracle arithmetic stays float32
-    because numpy would otherwise promote python floats... python floats are
-    weak scalars under NEP 50, so nothing to do); kept for clarity."""
-    return table
 
 
 def rms(y_last, w=None, ref=None):

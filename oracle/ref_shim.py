@@ -1,10 +1,15 @@
-"""Import shim for the LIVE reference (quartiq/rayopt at /root/reference).
+"""Import shim for the LIVE reference (quartiq/rayopt).
 
-TEST INFRASTRUCTURE ONLY.  Used in the build container (where /root/reference
-exists) to (a) pin the oracle restatements in this directory against the
-reference itself and (b) generate the golden fixtures under tests/golden/.
-It is never imported by the product (rayopt_b200/) and it cannot work on the
-GPU box (no /root/reference there).
+TEST / BENCH INFRASTRUCTURE ONLY.  Used to (a) pin the oracle restatements in
+this directory against the reference itself, (b) generate the golden fixtures
+under tests/golden/, (c) run the reference's own GeometricTrace / System next
+to (and bound to) the CUDA engine in the ``-m gpu`` tests and (d) time the
+reference's CPU path in bench.py (``cpu_baseline`` / ``--impl reference``).
+It is never imported by the product (rayopt_b200/).
+
+Where the reference comes from: /root/reference in the build container; on the
+GPU box (no /root/reference) the byte-for-byte copy staged by
+oracle/make_ref.py under the git-ignored oracle/_ref/.
 
 Recipe: stub `fastcache`, register a synthetic package
 `rayopt` whose __path__ is the reference tree so that rayopt/__init__.py (which
@@ -17,11 +22,22 @@ import sys
 import types
 import warnings
 
-REFERENCE_ROOT = os.environ.get("RAYOPT_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _root():
+    env = os.environ.get("RAYOPT_REFERENCE")
+    for cand in (env, "/root/reference", os.path.join(HERE, "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "rayopt", "geometric_trace.py")):
+            return cand
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _root()
 
 
 def available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "rayopt"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "rayopt", "geometric_trace.py"))
 
 
 def load():

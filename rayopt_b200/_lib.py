@@ -34,6 +34,8 @@ SYMBOLS = {
     "rtx_host_free": (_i, [_vp, _vp]),
     "rtx_memcpy_h2d": (_i, [_vp, _vp, _vp, _sz]),
     "rtx_memcpy_d2h": (_i, [_vp, _vp, _vp, _sz]),
+    "rtx_memcpy_d2d": (_i, [_vp, _vp, _vp, _sz]),
+    "rtx_numa_bind": (_i, [_vp, _i, C.POINTER(_i)]),
     "rtx_memcpy2d_d2h": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _sz]),
     "rtx_memset": (_i, [_vp, _vp, _i, _sz]),
     "rtx_timer_start": (_i, [_vp]),
@@ -56,7 +58,8 @@ SYMBOLS = {
     "rtx_ipc_export": (_i, [_vp, _vp, _vp]),
     "rtx_ipc_open": (_i, [_vp, _vp, _pp]),
     "rtx_ipc_close": (_i, [_vp, _vp]),
-    "rtx_trace_gather": (_i, [_vp, _vp, _i, _vp, _i, _i64, _vp, _vp, _i, _i, _vp, _i64, _u]),
+    "rtx_trace_gather": (_i, [_vp, _vp, _i, _vp, _i, _i64, _vp, _vp, _i, _i, _vp, _vp, _i64,
+                              _u]),
 }
 
 _lib = None

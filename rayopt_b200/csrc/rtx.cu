@@ -5,6 +5,11 @@
 #include "../../include/rtx.h"
 #include "rtx_device.cuh"
 
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -74,6 +79,9 @@ struct rtx_ctx {
     unsigned* mask = nullptr; // rtx_set_mask_output
     void* tsum = nullptr;     // rtx_set_path_sum_output
     int tsum_upto = 0;
+    // rtx_numa_bind: what to restore
+    bool numa_bound = false;
+    cpu_set_t saved_affinity;
     bool tuned = false;       // an RTX_* environment knob overrides the heuristics
     int tune = 1;             // TraceParams::tune bits (RTX_TUNE); 1 = L2 evict_first stores
 };
@@ -280,6 +288,8 @@ struct PeerDst {
     int n = 0;
     long long off = 0;
     void* ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* ptr_i[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool has_i = false;
 };
 
 template <typename T>
@@ -314,11 +324,17 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
     if (peers && peers->n > 0) {
         p.npeer = peers->n;
         p.peer_off = peers->off;
-        for (int k = 0; k < peers->n; ++k) p.peer[k] = (T*)peers->ptr[k];
+        p.peer_has_i = peers->has_i ? 1 : 0;
+        for (int k = 0; k < peers->n; ++k) {
+            p.peer[k] = (T*)peers->ptr[k];
+            p.peer_i[k] = (T*)peers->ptr_i[k];
+        }
         // bulk stores need 16-byte aligned runs in every destination
         peers_ok = (peers->off * 3 * (long long)sizeof(T)) % 16 == 0;
-        for (int k = 0; k < peers->n; ++k)
+        for (int k = 0; k < peers->n; ++k) {
             peers_ok = peers_ok && (reinterpret_cast<uintptr_t>(peers->ptr[k]) & 15u) == 0;
+            peers_ok = peers_ok && (reinterpret_cast<uintptr_t>(peers->ptr_i[k]) & 15u) == 0;
+        }
     }
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     int rpt = ctx->default_rpt;
@@ -368,6 +384,11 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
         nbuf = 2;
     }
     if (!(aligned && ld % (32 * rpt) == 0)) store = STORE_DIRECT;
+    // The staged paths write whole 32*rpt-ray groups.  Into a gather buffer
+    // that is only safe when the shard is a whole number of groups: a ragged
+    // tail would spill clamped copies of the last ray into the next rank's
+    // range (a race with that rank's own stores) -- per-ray stores instead.
+    if (p.npeer > 0 && N % (32 * rpt) != 0) store = STORE_DIRECT;
     if (batch && batch->n > 0) {
         p.nbatch = batch->n;
         for (int b = 0; b < batch->n; ++b) p.item[b] = batch->item[b];
@@ -595,7 +616,6 @@ const char* rtx_strerror(int code) {
         case RTX_E_BADARG: return "rtx: bad argument";
         case RTX_E_UNSUPPORTED: return "rtx: unsupported (too many aspheric coefficients / surfaces, or RTX_EXACT with FP32)";
         case RTX_E_NOMEM: return "rtx: out of memory";
-        case RTX_E_NCCL: return "rtx: NCCL error";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
@@ -735,8 +755,65 @@ int rtx_host_alloc(rtx_ctx* ctx, size_t bytes, void** hptr) {
     return 0;
 }
 int rtx_host_free(rtx_ctx* ctx, void* hptr) {
-    if (!ctx) return RTX_E_BADARG;
+    (void)ctx;  // page-locked memory may outlive the context that allocated it
     CK(cudaFreeHost(hptr));
+    return 0;
+}
+
+int rtx_numa_bind(rtx_ctx* ctx, int enable, int* node_out) {
+    if (!ctx) return RTX_E_BADARG;
+    if (node_out) *node_out = -1;
+    if (!enable) {
+        if (ctx->numa_bound) {
+            sched_setaffinity(0, sizeof(cpu_set_t), &ctx->saved_affinity);
+            syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+            ctx->numa_bound = false;
+        }
+        return 0;
+    }
+    char bus[32] = {0};
+    CK(cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), ctx->device));
+    for (char* c = bus; *c; ++c) *c = (char)tolower((unsigned char)*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    int node = -1;
+    if (FILE* f = fopen(path, "r")) {
+        if (fscanf(f, "%d", &node) != 1) node = -1;
+        fclose(f);
+    }
+    if (node < 0 || node >= 1024) return 0;  // not reported: leave everything alone
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int ncpu = 0;
+    if (FILE* f = fopen(path, "r")) {  // "0-31,64-95"
+        int a = 0, b = 0;
+        while (fscanf(f, "%d", &a) == 1) {
+            b = a;
+            int ch = fgetc(f);
+            if (ch == '-') {
+                if (fscanf(f, "%d", &b) != 1) b = a;
+                ch = fgetc(f);
+            }
+            for (int c = a; c <= b && c < CPU_SETSIZE; ++c) {
+                CPU_SET(c, &set);
+                ++ncpu;
+            }
+            if (ch != ',') break;
+        }
+        fclose(f);
+    }
+    if (ncpu == 0) return 0;
+    if (!ctx->numa_bound) sched_getaffinity(0, sizeof(cpu_set_t), &ctx->saved_affinity);
+    // only CPUs this process may use anyway (cgroup / taskset limits)
+    cpu_set_t both;
+    CPU_AND(&both, &set, &ctx->saved_affinity);
+    if (CPU_COUNT(&both) > 0) sched_setaffinity(0, sizeof(cpu_set_t), &both);
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, 8 * sizeof(mask));
+    ctx->numa_bound = true;
+    if (node_out) *node_out = node;
     return 0;
 }
 int rtx_memcpy_h2d(rtx_ctx* ctx, void* dst, const void* src, size_t bytes) {
@@ -747,6 +824,11 @@ int rtx_memcpy_h2d(rtx_ctx* ctx, void* dst, const void* src, size_t bytes) {
 int rtx_memcpy_d2h(rtx_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (!ctx) return RTX_E_BADARG;
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+int rtx_memcpy_d2d(rtx_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return RTX_E_BADARG;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return 0;
 }
 int rtx_memcpy2d_d2h(rtx_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch,
@@ -951,7 +1033,7 @@ int rtx_ipc_close(rtx_ctx* ctx, void* dptr) {
 
 int rtx_trace_gather(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0, int dtype,
                      int64_t N, const void* y0, const void* u0, int clip, int npeers,
-                     void* const* dst, int64_t dst_offset, unsigned flags) {
+                     void* const* dst, void* const* dst_i, int64_t dst_offset, unsigned flags) {
     if (!ctx) return RTX_E_BADARG;
     int rc = check_table(surf, S);
     if (rc) return rc;
@@ -962,9 +1044,11 @@ int rtx_trace_gather(rtx_ctx* ctx, const rtx_surface* surf, int S, const double*
     PeerDst pd;
     pd.n = npeers;
     pd.off = dst_offset;
+    pd.has_i = dst_i != nullptr;
     for (int k = 0; k < npeers; ++k) {
-        if (!dst[k]) return RTX_E_BADARG;
+        if (!dst[k] || (dst_i && !dst_i[k])) return RTX_E_BADARG;
         pd.ptr[k] = dst[k];
+        if (dst_i) pd.ptr_i[k] = dst_i[k];
     }
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventRecord(ctx->k0, ctx->stream));

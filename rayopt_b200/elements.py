@@ -23,8 +23,14 @@ class _Bare:
     offset = (0., 0., 0.)
     rotated = False
 
-    def __init__(self, e):
+    def __init__(self, e, mu=None):
         self._e = e
+        if mu is not None:
+            # explicit mu (Element.intercept / refract signatures carry no
+            # wavelength): the material must not be evaluated -- a dispersive
+            # one would need `l` (the reference's intercept(y, u) needs none,
+            # conjugates.py:254)
+            self.get_n_mu = lambda n0, l: (n0, mu)
 
     def __getattr__(self, k):
         return getattr(self._e, k)
@@ -32,9 +38,7 @@ class _Bare:
 
 def _record(element, n0, l, mu=None):
     t = np.zeros(1, SURFACE_DTYPE)
-    n = pack_element(t[0], _Bare(element), n0, l)
-    if mu is not None:                      # explicit mu (Element.refract signature)
-        t["mu"], t["muf"], t["sgn"], t["mu2m1"] = mu, abs(mu), np.sign(mu), mu**2 - 1
+    n = pack_element(t[0], _Bare(element, mu), n0, l)
     return t, n
 
 

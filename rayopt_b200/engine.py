@@ -38,9 +38,10 @@ class DeviceArray:
         engine._live[id(self)] = self.ptr
 
     def free(self):
-        if self.ptr is not None and self.engine.ctx is not None:
-            check(self.engine.lib.rtx_free_device(self.engine.ctx, self.ptr))
-            self.engine._live.pop(id(self), None)
+        eng = self.engine
+        if self.ptr is not None and eng.ctx is not None and id(self) in eng._live:
+            eng._live.pop(id(self), None)
+            check(eng.lib.rtx_free_device(eng.ctx, self.ptr))
         self.ptr = None
 
     def __del__(self):              # dropped without free(): give the HBM back
@@ -64,6 +65,12 @@ class DeviceArray:
         self.engine.sync()
         return out
 
+    def copy_from(self, other, nbytes=None):
+        """device-to-device copy (asynchronous on the engine stream)"""
+        n = min(self.nbytes, other.nbytes) if nbytes is None else int(nbytes)
+        check(self.engine.lib.rtx_memcpy_d2d(self.engine.ctx, self.ptr, other.ptr, n))
+        return self
+
     def rows(self, r0, r1=None):
         """byte-offset view of leading-axis rows (no copy)"""
         v = object.__new__(DeviceArray)
@@ -74,11 +81,28 @@ class DeviceArray:
         v.nbytes = row_bytes*(r1 - r0)
         v.ptr = self.ptr + r0*row_bytes
         v.free = lambda: None
+        v._parent = self            # keeps the allocation alive
         return v
 
 
+class _PinnedBlock:
+    """owner of one page-locked allocation: the numpy arrays handed out by
+    Engine.pinned_empty are views of its buffer, so the memory is released
+    (cudaFreeHost) only when the LAST view has died -- never under a live
+    array, whatever happens to the trace object or the engine"""
+
+    def __init__(self, lib, address, nbytes):
+        self.address = address
+        self.buf = (C.c_char*nbytes).from_address(address)
+        weakref.finalize(self.buf, lib.rtx_host_free, None, address)
+
+
 class Engine:
-    def __init__(self, device=0):
+    def __init__(self, device=0, numa=None):
+        """`numa`: pin this process to the CPUs / memory of the GPU's NUMA
+        node (rtx_numa_bind) so that page-locked buffers are local to the
+        GPU's PCIe root; default: only in one-process-per-GPU launches
+        (LOCAL_RANK set)."""
         self.lib = _lib.load()
         self.ctx = None
         if self.lib.rtx_device_count() < 1:
@@ -89,32 +113,48 @@ class Engine:
         self.ctx = ctx
         self.device = int(device)
         self._live = {}
-        self._pinned = {}
+        self.numa_node = None
+        import os
+        if numa is None:
+            numa = "LOCAL_RANK" in os.environ
+        if numa:
+            self.numa_bind(True)
         sm, fr, tot = C.c_int(), C.c_size_t(), C.c_size_t()
         name = C.create_string_buffer(128)
         check(self.lib.rtx_device_info(self.ctx, C.byref(sm), C.byref(fr), C.byref(tot), name, 128))
         self.sm_count, self.total_bytes = sm.value, tot.value
         self.name = name.value.decode()
-        self._fin = weakref.finalize(self, Engine._finalize, self.lib, self.ctx)
+        self._fin = weakref.finalize(self, Engine._finalize, self.lib, self.ctx, self._live)
 
     @staticmethod
-    def _finalize(lib, ctx):
+    def _finalize(lib, ctx, live):
+        # (also runs at interpreter exit) `live` is emptied first so that a
+        # DeviceArray collected later sees "not mine any more" and never hands
+        # the dangling context back to the library
         try:
+            live.clear()
             lib.rtx_free(ctx)
         except Exception:
             pass
 
     def close(self):
+        """Release the context and every DeviceArray still alive.  Page-locked
+        arrays from pinned_empty stay valid: they are freed when their last
+        numpy view dies."""
         if self.ctx is not None:
-            for p in list(self._pinned.values()):
-                self.lib.rtx_host_free(self.ctx, p)
-            self._pinned.clear()
             for p in list(self._live.values()):     # device arrays still alive
                 self.lib.rtx_free_device(self.ctx, p)
             self._live.clear()
             self._fin.detach()
             self.lib.rtx_free(self.ctx)
             self.ctx = None
+
+    def numa_bind(self, enable=True):
+        """rtx_numa_bind: returns the NUMA node (or -1 if not reported)"""
+        node = C.c_int(-1)
+        check(self.lib.rtx_numa_bind(self.ctx, int(bool(enable)), C.byref(node)))
+        self.numa_node = node.value if enable else None
+        return node.value
 
     # ---- memory -------------------------------------------------------
     def empty(self, shape, dtype=np.float64):
@@ -130,15 +170,12 @@ class Engine:
         n = int(np.prod(shape, dtype=np.int64))*dtype.itemsize
         p = C.c_void_p()
         check(self.lib.rtx_host_alloc(self.ctx, max(n, 16), C.byref(p)))
-        buf = (C.c_char*max(n, 16)).from_address(p.value)
-        a = np.frombuffer(buf, dtype=dtype, count=n//dtype.itemsize).reshape(shape)
-        self._pinned[a.ctypes.data] = p.value
-        return a
+        block = _PinnedBlock(self.lib, p.value, max(n, 16))
+        # the array's base chain holds block.buf: freed with the last view
+        return np.frombuffer(block.buf, dtype=dtype, count=n//dtype.itemsize).reshape(shape)
 
-    def pinned_free(self, a):
-        p = self._pinned.pop(a.ctypes.data, None)
-        if p is not None:
-            check(self.lib.rtx_host_free(self.ctx, p))
+    def memset(self, darray, value=0):
+        check(self.lib.rtx_memset(self.ctx, darray.ptr, int(value), darray.nbytes))
 
     def free_bytes(self):
         fr = C.c_size_t()
@@ -271,17 +308,24 @@ class Engine:
         return tuple(res)
 
     def trace_gather(self, table, y0, u0, dst_ptrs, dst_offset, N=None, clip=False,
-                     rot0=None, exact=False):
-        """rtx_trace_gather: trace the local shard (DEVICE y0,u0) and bulk-store
+                     rot0=None, exact=False, dst_i_ptrs=None):
+        """rtx_trace_gather: trace the local shard (DEVICE y0,u0) and store
         the last surface's intercepts into every buffer of `dst_ptrs` (raw
-        device pointers: local or peer memory) at ray offset `dst_offset`."""
+        device pointers: local or peer memory) at ray offset `dst_offset`;
+        `dst_i_ptrs`: a second set of buffers for the incidence directions."""
         table = self._table(table)
         N = y0.shape[0] if N is None else int(N)
         r0 = None if rot0 is None else np.ascontiguousarray(rot0, np.float64).reshape(9)
         arr = (C.c_void_p*len(dst_ptrs))(*[C.c_void_p(int(p)) for p in dst_ptrs])
+        arr_i = None
+        if dst_i_ptrs is not None:
+            if len(dst_i_ptrs) != len(dst_ptrs):
+                raise ValueError("dst_i_ptrs must match dst_ptrs")
+            arr_i = C.cast((C.c_void_p*len(dst_ptrs))(*[C.c_void_p(int(p)) for p in dst_i_ptrs]),
+                           C.c_void_p)
         check(self.lib.rtx_trace_gather(
             self.ctx, ptr(table), len(table), ptr(r0), _code(y0.dtype), N, y0.ptr, u0.ptr,
-            int(bool(clip)), len(dst_ptrs), C.cast(arr, C.c_void_p), int(dst_offset),
+            int(bool(clip)), len(dst_ptrs), C.cast(arr, C.c_void_p), arr_i, int(dst_offset),
             self._flags(exact, False)))
 
     def ipc_export(self, darray):
@@ -298,15 +342,39 @@ class Engine:
     def ipc_close(self, p):
         check(self.lib.rtx_ipc_close(self.ctx, p))
 
-    def aim_infinite_device(self, yo, z, p, angle, yp=None, nrays=None, dtype=np.float64):
+    def download_rays(self, darray, idx):
+        """host copy of rays `idx` (1-d integer array) of a device array whose
+        trailing axes are (rays, 3) -- a row view (1, ld, 3) or an (N, 3)
+        array: one strided D2H when `idx` is an arithmetic progression, else one
+        24-byte copy per ray (samples for parity checks)"""
+        idx = np.asarray(idx, np.int64).reshape(-1)
+        item = darray.dtype.itemsize*3
+        out = np.empty((len(idx), 3), darray.dtype)
+        if len(idx) == 0:
+            return out
+        step = int(idx[1] - idx[0]) if len(idx) > 1 else 1
+        if len(idx) > 1 and step > 0 and np.all(np.diff(idx) == step):
+            check(self.lib.rtx_memcpy2d_d2h(self.ctx, ptr(out), item, darray.ptr + int(idx[0])*item,
+                                            step*item, item, len(idx)))
+        else:
+            for j, i in enumerate(idx):
+                check(self.lib.rtx_memcpy_d2h(self.ctx, out[j].ctypes.data_as(C.c_void_p),
+                                              darray.ptr + int(i)*item, item))
+        self.sync()
+        return out
+
+    def aim_infinite_device(self, yo, z, p, angle, yp=None, nrays=None, dtype=np.float64,
+                            rings=None):
         """Launch rays of an aimed bundle generated in HBM (rtx_aim_infinite):
         `yp` a DEVICE (N,2) array of pupil coordinates, or None for the
-        hexapolar grid with about `nrays` rays.  Returns DeviceArrays (y0, u0)."""
+        hexapolar grid with about `nrays` rays (or exactly `rings` rings).
+        Returns DeviceArrays (y0, u0)."""
         from .rays import aim_frame
         frame = np.ascontiguousarray(np.concatenate(aim_frame(yo, z, angle)), np.float64)
         pmax = float(np.fabs(np.asarray(p, float)).max())
         if yp is None:
-            rings = int(np.sqrt(nrays/3. - 1/12.) - 1/2.)
+            if rings is None:
+                rings = int(np.sqrt(nrays/3. - 1/12.) - 1/2.)
             N = 1 + 3*rings*(rings + 1)
         else:
             rings, N = 0, yp.shape[0]
@@ -360,7 +428,8 @@ class Engine:
     def rms(self, y, w=None, N=None, ref_point=None, comm_sum=None):
         """GeometricTrace.rms (rayopt/geometric_trace.py:171-183) of device
         intercepts `y` (N,3) without a D2H of the rays: centre = unweighted
-        mean (or `ref_point`), rms = sqrt(sum w |y - y0|^2).  Like the
+        mean (or `ref_point`), rms = sqrt(sum w |y - y0|^2) with the
+        reference's default weights 1/N when `w` is None.  Like the
         reference it is NOT NaN-masked: any non-finite ray gives NaN.
         `comm_sum` (callable: 8-vector -> summed 8-vector) makes it the rms of
         a ray-sharded bundle (one all-reduce per pass)."""
@@ -373,7 +442,7 @@ class Engine:
         m = red(self.moments(y, w, N, center=ref_point))
         if m[4] != m[5]:
             return float("nan")
-        return float(np.sqrt(m[3]))
+        return float(np.sqrt(m[3]/m[5] if w is None else m[3]))
 
 
     def refocus_shift(self, y, inc, w=None, N=None, comm_sum=None):

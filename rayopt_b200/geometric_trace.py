@@ -14,13 +14,14 @@ Two ways to use it:
 * ``bind(rayopt.GeometricTrace)`` returns a subclass of the reference class
   whose ``allocate``/``propagate`` are replaced, so that ``rays_point``,
   ``rays_clipping``, ``refocus``, ``opd``, ``Analysis`` ... keep working
-  unchanged (INTEGRATION.md).
+  unchanged.  ``bind(..., resident=True)`` keeps the results
+  in HBM instead (``y,u,i,t`` are ``LazyRows``, lazy.py): the consumers above
+  read single rows, so only those cross PCIe.
 """
-import weakref
-
 import numpy as np
 
 from .engine import default_engine
+from .lazy import ResidentMixin
 from .surface_table import pack_system
 
 # result arrays above this size are allocated page-locked so that the D2H of a
@@ -42,12 +43,11 @@ class PropagateMixin:
         return self.engine
 
     def _empty(self, shape):
-        n = int(np.prod(shape))*8
-        if n >= PINNED_THRESHOLD:
-            eng = self._engine()
-            a = eng.pinned_empty(shape, np.float64)
-            weakref.finalize(self, _release, weakref.ref(eng), a.ctypes.data)
-            return a
+        # page-locked memory is owned by the arrays themselves (freed when the
+        # last view dies, Engine.pinned_empty): a row kept by the caller stays
+        # valid after the trace object is gone or re-allocated
+        if int(np.prod(shape))*8 >= PINNED_THRESHOLD:
+            return self._engine().pinned_empty(shape, np.float64)
         return np.empty(shape)
 
     # For unrotated systems the incidence array is redundant: i[j] (direction
@@ -122,14 +122,6 @@ class PropagateMixin:
             if not alias:
                 self.i[sl] = I
         self.n[sl] = n
-
-
-def _release(engine_ref, address):
-    eng = engine_ref()
-    if eng is not None and eng.ctx is not None:
-        p = eng._pinned.pop(address, None)
-        if p is not None:
-            eng.lib.rtx_host_free(eng.ctx, p)
 
 
 class GeometricTrace(PropagateMixin):
@@ -248,16 +240,25 @@ class GeometricTrace(PropagateMixin):
         self.propagate()
 
 
-def bind(reference_trace_class, engine=None, dtype=np.float64, exact=False):
+def bind(reference_trace_class, engine=None, dtype=np.float64, exact=False, resident=False,
+         alias_incidence=True):
     """Subclass of the reference's GeometricTrace with the hot path replaced.
 
         import rayopt, rayopt_b200
         GT = rayopt_b200.bind(rayopt.GeometricTrace)
         t = GT(system); t.rays_point((0, 1.), nrays=10**6, distribution="hexapolar")
+
+    `resident=True`: the trace stays in HBM (``ResidentMixin``); ``t.y[-1]``,
+    ``t.i[-1]``, ``t.rms()``, ``t.refocus()`` ... fetch or reduce single rows.
     """
-    return type("GeometricTrace", (PropagateMixin, reference_trace_class),
-                {"engine": engine, "dtype": dtype, "exact": exact,
-                 "__doc__": reference_trace_class.__doc__})
+    attrs = {"engine": engine, "exact": exact, "alias_incidence": alias_incidence,
+             "__doc__": reference_trace_class.__doc__}
+    if resident:
+        if np.dtype(dtype) != np.float64:
+            raise ValueError("the resident drop-in is FP64")
+        return type("GeometricTrace", (ResidentMixin, reference_trace_class), attrs)
+    attrs["dtype"] = dtype
+    return type("GeometricTrace", (PropagateMixin, reference_trace_class), attrs)
 
 
 def system_propagate(system, y, u, n, l, start=1, stop=None, clip=False,

@@ -31,6 +31,24 @@ def hexapolar(nrays):
     return n, np.concatenate(l, axis=1).T
 
 
+def hexapolar_xy(idx, rings):
+    """pupil coordinates of rays `idx` of the hexapolar grid with `rings`
+    rings (rayopt/utils.py:174-180) without building the whole grid: ray 0 on
+    axis; ring i = 1..rings holds rays 3 i (i-1) < j <= 3 i (i+1) at angles
+    k 2 pi/(6 i) -- the index arithmetic of the device generator (pupil_xy in
+    rtx_device.cuh), used to check samples of 1e8-ray device-generated bundles"""
+    idx = np.asarray(idx, np.int64)
+    i = np.floor((1 + np.sqrt(1 + 4*np.maximum(idx - 1, 0)/3.))/2).astype(np.int64)
+    i = np.where(3*i*(i + 1) < idx, i + 1, i)
+    i = np.where(3*i*(i - 1) >= idx, i - 1, i)
+    i = np.maximum(i, 1)
+    k = idx - 1 - 3*i*(i - 1)
+    a = k*(2*np.pi/(6*i))
+    xy = np.c_[np.sin(a)*i/rings, np.cos(a)*i/rings]
+    xy[idx == 0] = 0
+    return xy
+
+
 def aim_frame(yo, z, angle):
     """The per-field constants of aim_infinite: (u, ybase, s, m), each (3,):
     the common ray direction, yz - z*u, and the normalised sagittal and

@@ -32,7 +32,7 @@ def test_header_symbols_all_exported(lib):
 
 
 def test_abi_version_and_layout(lib):
-    assert lib.rtx_abi_version() == 1
+    assert lib.rtx_abi_version() == 2
     assert lib.rtx_sizeof_surface() == SURFACE_DTYPE.itemsize
 
 

@@ -264,11 +264,20 @@ class FakeDeviceArray:
         return FakeDeviceArray(self.a[r0:(r0 + 1 if r1 is None else r1)])
 
     def upload(self, v):
-        self.a[...] = np.asarray(v).reshape(self.a.shape)
+        v = np.asarray(v, self.a.dtype)
+        self.a.reshape(-1)[:v.size] = v.reshape(-1)      # leading bytes, like the H2D copy
         return self
 
     def download(self, out=None):
-        return self.a.copy()
+        if out is None:
+            return self.a.copy()
+        out.reshape(-1)[:] = self.a.reshape(-1)[:out.size]
+        return out
+
+    def copy_from(self, other, nbytes=None):
+        n = min(self.a.size, other.a.size) if nbytes is None else nbytes//self.a.itemsize
+        self.a.reshape(-1)[:n] = other.a.reshape(-1)[:n]
+        return self
 
     def free(self):
         pass
@@ -285,11 +294,25 @@ class FakeResidentEngine:
                      exact=False, **kw):
         res = np_oracle.trace(table, y0.a[0, :N], u0.a[0, :N], clip=clip, rot0=rot0)
         for dst, src in zip((Y, U, I, T), res):
-            dst.a[:, :N] = src
+            if dst is not None:
+                dst.a[:, :N] = src
+
+    def sync(self):
+        pass
 
     def rms(self, y, w, N=None, ref_point=None):
-        return np_oracle.rms(y.a[0, :N], None if w is None else w.a,
-                             ref=None) if ref_point is None else float("nan")
+        yy = y.a[0, :N, :2]
+        c = yy.mean(0) if ref_point is None else np.asarray(ref_point)
+        ww = np.ones(N)/N if w is None else w.a
+        return float(np.sqrt((np.square(yy - c).sum(1)*ww).sum()))
+
+    def refocus_shift(self, y, inc, w=None, N=None):
+        yy, ii = y.a[0, :N, :2], inc.a[0, :N]
+        uu = ii[:, :2]/ii[:, 2:]
+        ok = np.isfinite(uu).all(1)
+        yy, uu = yy[ok] - yy[ok].mean(0), uu[ok] - uu[ok].mean(0)
+        ww = np.ones(len(yy)) if w is None else w.a[ok]
+        return float(-(ww[:, None]*yy*uu).sum()/(ww[:, None]*uu*uu).sum())
 
 
 def test_resident_trace_host_logic_on_cpu():
@@ -314,6 +337,50 @@ def test_resident_trace_host_logic_on_cpu():
     want = np_oracle.trace(c["table"][3:8], g.y[3], g.u[3], clip=False)
     assert np.array_equal(g.y[4:9], want[0], equal_nan=True)
     assert abs(g.rms(3) - np_oracle.rms(g.y[3], c["w"])) < 1e-15
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+def test_bound_resident_class_matches_reference():
+    """bind(rayopt.GeometricTrace, resident=True) on the numpy stand-in of the
+    device: the reference's rays_point / rays_clipping / rays_paraxial / opd
+    run on LazyRows, rms / refocus on the (fake) device reductions"""
+    warnings.simplefilter("ignore")
+    R = ref_shim.load()
+
+    def system():
+        s = R.System(**yaml.safe_load(systems_yaml.DOUBLE_GAUSS))
+        s.update()
+        s.paraxial.refocus()
+        s[-1].distance += .3
+        return s
+    s1, s2 = system(), system()
+    GT = bind(R.GeometricTrace, engine=FakeResidentEngine(), resident=True)
+    for fn, args, kw in (("rays_point", ((0, .7),), dict(nrays=150, distribution="hexapolar", clip=True)),
+                         ("rays_point", ((0, 1.),), dict(nrays=31, distribution="tee", clip=True)),
+                         ("rays_clipping", ((0, 1.),), {}), ("rays_paraxial", (), {})):
+        ref, got = R.GeometricTrace(s1), GT(s2)
+        getattr(ref, fn)(*args, **kw)
+        getattr(got, fn)(*args, **kw)
+        for k in "yuit":
+            assert np.array_equal(np.asarray(getattr(got, k)), getattr(ref, k), equal_nan=True), (fn, k)
+        assert np.array_equal(got.n, ref.n) and got.ref == ref.ref
+        assert got._i_alias and got.y.shape == ref.y.shape
+    ref, got = R.GeometricTrace(s1), GT(s2)
+    for t in (ref, got):
+        t.rays_point((0, .7), nrays=200, distribution="hexapolar", clip=True, filter=False)
+    d0 = s1[-1].distance
+    ref.refocus()
+    got.refocus()
+    assert abs(s1[-1].distance - d0) > 1e-3
+    assert abs(s1[-1].distance - s2[-1].distance) < 1e-12
+    for t in (ref, got):
+        t.rays_point((0, 0.), nrays=100, distribution="hexapolar")
+    assert abs(got.rms() - ref.rms()) < 1e-14 and abs(got.rms(ref=0) - ref.rms(ref=0)) < 1e-14
+    for a, b in zip(got.opd(resample=False), ref.opd(resample=False)):
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-9)
+    # item assignment writes through (the reference's own rays_given would use it)
+    got.y[0, :, 1] = 7.
+    assert np.all(got.y[0][:, 1] == 7.) and np.all(got._dev["y"].a[0, :got.nrays, 1] == 7.)
 
 
 @pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")

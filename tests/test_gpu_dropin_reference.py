@@ -1,0 +1,232 @@
+"""The drop-in wiring ON HARDWARE against the REAL reference.
+
+The reference (staged under oracle/_ref by oracle/make_ref.py, or
+/root/reference) runs on the host; its own ``GeometricTrace`` / ``System``
+classes are bound to the CUDA engine with ``rayopt_b200.bind`` /
+``rayopt_b200.install`` and driven through the reference's own call patterns:
+
+* ``rays_point`` / ``rays_clipping`` / ``rays_line`` / ``refocus`` / ``rms`` /
+  ``opd``                      rayopt/geometric_trace.py:82-144,171-229
+* ``System.aim_chief`` / ``aim_marginal`` / ``pupil``   rayopt/system.py:507-593
+  (hundreds of 1-3 ray traces through the small-bundle CUDA path)
+* the consumers of ``Analysis``  rayopt/analysis.py:231-245,269-280
+  (``y[-1]``, ``i[-1]``, ``y[0]``, ``u[0]`` of tee / hexapolar bundles)
+* the reference's own integration tests rayopt/test/test_raytrace.py:151-199
+
+RTX_EXACT results must be BIT-IDENTICAL to the reference on the unrotated
+analytic lenses; the default fast mode within 1e-10 (SURVEY 8d comparator).
+"""
+import warnings
+
+import numpy as np
+import pytest
+import yaml
+
+import ref_shim
+import systems_yaml
+from conftest import assert_parity
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not ref_shim.available(),
+                                 reason="no reference tree (run oracle/make_ref.py where "
+                                        "/root/reference exists)")]
+
+
+@pytest.fixture(scope="module")
+def R():
+    warnings.simplefilter("ignore")
+    np.seterr(all="ignore")
+    return ref_shim.load()
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from rayopt_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def build(R, name, cls=None, defocus=0.):
+    s = (cls or R.System)(**yaml.safe_load(systems_yaml.SYSTEMS[name]))
+    s.update()
+    s.paraxial.refocus()
+    if defocus:
+        s[-1].distance += defocus
+    return s
+
+
+def same(got, ref, exact, what=""):
+    for k in "yuit":
+        a, b = np.asarray(getattr(got, k)), getattr(ref, k)
+        if exact:
+            assert np.array_equal(a, b, equal_nan=True), (what, k)
+        else:
+            assert_parity(a, b, 1e-10, "%s %s" % (what, k))
+    assert np.array_equal(got.n, ref.n), what
+
+
+CALLS = [
+    ("rays_point", ((0, 1.),), dict(nrays=300, distribution="hexapolar", clip=True)),
+    ("rays_point", ((0, .7),), dict(nrays=152, distribution="tee", clip=True)),
+    ("rays_point", ((0, .5),), dict(nrays=9, distribution="meridional")),
+    ("rays_point", ((0, 1.),), dict(nrays=13, distribution="radau", filter=False)),
+    ("rays_clipping", ((0, 1.),), {}),
+    ("rays_line", ((0, 1.),), dict(nrays=5)),
+    ("rays_paraxial", (), {}),
+]
+
+
+@pytest.mark.parametrize("resident", [False, True])
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("lens", ["cooke", "double_gauss"])
+def test_bound_reference_trace_on_cuda(R, eng, lens, exact, resident):
+    """bind(rayopt.GeometricTrace): the reference's own ray-launch helpers run
+    on the CUDA engine (host arrays, or resident LazyRows) and reproduce the
+    reference's trace of the same System"""
+    from rayopt_b200 import bind
+    s = build(R, lens)
+    GT = bind(R.GeometricTrace, engine=eng, exact=exact, resident=resident)
+    l0 = eng.launch_count()
+    for fn, args, kw in CALLS:
+        ref, got = R.GeometricTrace(s), GT(s)
+        getattr(ref, fn)(*args, **kw)
+        getattr(got, fn)(*args, **kw)
+        same(got, ref, exact, "%s %s %s" % (lens, fn, kw.get("distribution", "")))
+        assert got.ref == ref.ref and np.array_equal(got.w, ref.w)
+        assert np.array_equal(got.path, ref.path) and np.array_equal(got.origins, ref.origins)
+    assert eng.launch_count() - l0 >= len(CALLS)
+
+
+@pytest.mark.parametrize("resident", [False, True])
+def test_refocus_rms_opd_of_the_reference_class_on_cuda(R, eng, resident):
+    """refocus (geometric_trace.py:82-99), rms (:171-183) and opd (:101-144) of
+    the bound class against the reference on a defocused lens"""
+    from rayopt_b200 import bind
+    s1, s2 = build(R, "double_gauss", defocus=.3), build(R, "double_gauss", defocus=.3)
+    GT = bind(R.GeometricTrace, engine=eng, exact=True, resident=resident)
+    ref, got = R.GeometricTrace(s1), GT(s2)
+    kw = dict(nrays=400, distribution="hexapolar", clip=True, filter=False)
+    ref.rays_point((0, .7), **kw)
+    got.rays_point((0, .7), **kw)
+    same(got, ref, True, "before refocus")
+    d0 = s1[-1].distance
+    ref.refocus()
+    got.refocus()
+    assert abs(s1[-1].distance - d0) > 1e-3               # it had work to do
+    assert abs((s1[-1].distance - d0) - (s2[-1].distance - d0)) < 1e-11
+    assert_parity(np.asarray(got.y)[-1:], ref.y[-1:], 1e-10, "after refocus")
+    # rms / opd need a bundle without vignetted rays
+    ref.rays_point((0, 0.), nrays=200, distribution="hexapolar", clip=False)
+    got.rays_point((0, 0.), nrays=200, distribution="hexapolar", clip=False)
+    assert abs(got.rms() - ref.rms()) < 1e-13
+    assert abs(got.rms(ref=0) - ref.rms(ref=0)) < 1e-13
+    assert abs(got.rms(3) - ref.rms(3)) < 1e-12
+    xr, yr, tr = ref.opd(resample=False)
+    xg, yg, tg = got.opd(resample=False)
+    np.testing.assert_allclose(tg, tr, rtol=0, atol=1e-9)  # waves
+    np.testing.assert_allclose(xg, xr, rtol=0, atol=1e-12)
+    if resident:
+        got.free()
+
+
+def test_analysis_consumers_read_single_rows(R, eng):
+    """what Analysis.transverse / spots read (analysis.py:231-245,269-280) from
+    a resident bound trace: only the rows asked for cross PCIe"""
+    from rayopt_b200 import bind
+    s = build(R, "cooke")
+    GT = bind(R.GeometricTrace, engine=eng, exact=True, resident=True)
+    tanarcsin = R.utils.tanarcsin
+    p = s.object.pupil.distance
+    for hi, wi in ((1., s.wavelengths[0]), (.707, s.wavelengths[2])):
+        ref, got = R.GeometricTrace(s), GT(s)
+        for t in (ref, got):
+            t.rays_point((0, hi), wi, nrays=152, distribution="tee", clip=True)
+        y, yr = got.y[-1, :, :2] - got.y[-1, got.ref, :2], ref.y[-1, :, :2] - ref.y[-1, ref.ref, :2]
+        assert np.array_equal(y, yr, equal_nan=True)
+        py = got.y[0, :, :2] + p*tanarcsin(got.u[0])
+        assert np.array_equal(py, ref.y[0, :, :2] + p*tanarcsin(ref.u[0]))
+        rows = len(s)
+        assert got.y.fetched_bytes == 2*got.nrays*24 and got.u.fetched_bytes == got.nrays*24
+        assert got.t.fetched_bytes == 0 and rows > 3
+        for t in (ref, got):
+            t.rays_point((0, hi), wi, nrays=150, distribution="hexapolar", clip=True)
+        assert np.array_equal(tanarcsin(got.i[-1]), tanarcsin(ref.i[-1]), equal_nan=True)
+        assert np.array_equal(got.y[-1], ref.y[-1], equal_nan=True)
+        got.free()
+
+
+def test_installed_system_aims_through_the_cuda_path(R, eng):
+    """install(System): aim_chief / aim_marginal (system.py:507-555) issue
+    their 1-3 ray traces through rtx_trace_host's small-bundle path; the pupil
+    solution equals the unpatched reference's, and the reference's own
+    integration tests (test_raytrace.py:151-199) pass on the patched classes"""
+    import rayopt_b200
+
+    class System(R.System):          # patched copies: leave the shared classes alone
+        pass
+
+    class Trace(R.GeometricTrace):
+        pass
+    rayopt_b200.install(System, Trace, engine=eng, exact=True)
+    s = build(R, "cooke", System)
+    s.paraxial.update_conjugates()
+    s0 = build(R, "cooke")
+    s0.paraxial.update_conjugates()
+    l0 = eng.launch_count()
+    for yo in ((0, 1.), (0, .5), (.3, .6)):
+        z1, p1 = s.pupil(yo)
+        z0, p0 = s0.pupil(yo)
+        np.testing.assert_allclose(z1, z0, rtol=1e-12)
+        np.testing.assert_allclose(p1, p0, rtol=1e-12)
+    z1, p1 = s.pupil((0, 1.), stop=-1)
+    z0, p0 = s0.pupil((0, 1.), stop=-1)
+    np.testing.assert_allclose(p1, p0, rtol=1e-12)
+    assert eng.launch_count() - l0 > 50           # aiming really ran on the GPU
+    g = Trace(s)
+    # test_aim_point
+    g.rays_point((0, 1.))
+    g.rays_clipping((0, 1.))
+    g.rays_line((0, 1.))
+    # test_aim_point_more
+    i = s.stop
+    r = np.array([el.radius for el in s[1:-1]])
+    g.rays_clipping((0, 1.))
+    np.testing.assert_allclose(g.u[0, :, :], g.u[0, (0,)*g.u.shape[1], :])
+    np.testing.assert_allclose(g.y[i, 0, 1], 0, atol=5e-3)
+    np.testing.assert_allclose(min(g.y[1:-1, 1, 1] + r), 0, atol=1e-3)
+    np.testing.assert_allclose(max(g.y[1:-1, 2, 1] - r), 0, atol=1e-3)
+    g.rays_point((0, 1.), distribution="cross", nrays=5, filter=False)
+    np.testing.assert_allclose(g.y[i, :3, 1]/s[i].radius, [-1, 0, 1], atol=1e-3, rtol=3e-2)
+    np.testing.assert_allclose(g.y[i, :, 0]/s[i].radius, [0, 0, 0, -1, 0, 1], atol=1e-1)
+    # test_quadrature: the known answer of the path
+    g.rays_point((0, 1.), nrays=13, distribution="radau", filter=False)
+    a = g.rms()
+    np.testing.assert_allclose(a, .052, rtol=1e-2)
+    g.rays_point((0, 1.), nrays=500, distribution="square", clip=False, filter=True)
+    np.testing.assert_allclose(a, g.rms(), rtol=5e-2)
+    # and the traces equal the unpatched reference's
+    g0 = R.GeometricTrace(s0)
+    g0.rays_point((0, 1.), nrays=13, distribution="radau", filter=False)
+    g.rays_point((0, 1.), nrays=13, distribution="radau", filter=False)
+    assert_parity(g.y, g0.y, 1e-10, "installed y")
+
+
+@pytest.mark.parametrize("lens,n", [("cooke_asph", 2000), ("mirror", 3000), ("zoom", 20000)])
+def test_bound_trace_other_lenses(R, eng, lens, n):
+    """aspheres (Newton), the folded mirror (rotated frames: `i` is a real
+    array) and the 20-surface zoom through the bound class, default fast mode"""
+    from rayopt_b200 import bind
+    s = build(R, lens)
+    GT = bind(R.GeometricTrace, engine=eng)
+    ref, got = R.GeometricTrace(s), GT(s)
+    rng = np.random.default_rng(3)
+    r, phi = np.sqrt(rng.random(n)), 2*np.pi*rng.random(n)
+    yp = np.c_[r*np.cos(phi), r*np.sin(phi)]
+    for t in (ref, got):
+        t.rays((0, .7), yp, s.wavelengths[0], clip=lens != "mirror", filter=False)
+    same(got, ref, False, lens)
+    res = bind(R.GeometricTrace, engine=eng, resident=True)(s)
+    res.rays((0, .7), yp, s.wavelengths[0], clip=lens != "mirror", filter=False)
+    same(res, ref, False, lens + " resident")
+    res.free()

@@ -320,31 +320,65 @@ def test_element_level_entry_points(eng):
     assert_parity(r[None], np_oracle.refract(one[0], wy[on], u0[on])[None], FP64_RTOL, "refract")
 
 
-@pytest.mark.parametrize("n", [70001, 3000])
-def test_trace_gather_epilogue(eng, systems, n):
-    """rtx_trace_gather: the last surface's intercepts are bulk-stored by the
+@pytest.mark.parametrize("with_i", [False, True])
+@pytest.mark.parametrize("n,off", [(70016, 192), (70001, 192), (3000, 64), (1000, 5)])
+def test_trace_gather_epilogue(eng, systems, n, off, with_i):
+    """rtx_trace_gather: the last surface's intercepts (and, optionally, its
+    incidence directions -- analysis.py:274-280 reads both) are stored by the
     trace kernel itself into several gather buffers at a ray offset (here two
-    local buffers stand in for peer GPUs; the 2-GPU NVLink run is
-    tests/gpu_scripts/multi_gpu_check.py)"""
+    local buffers stand in for peer GPUs; the NVLink runs are bench.py's C4 leg
+    and tests/gpu_scripts/multi_gpu_check.py).  Whatever N and the offset --
+    whole 64-ray groups (bulk stores) or ragged (per-ray fallback) -- EXACTLY
+    rays off .. off+N-1 are written: a shard never spills into its neighbour."""
     ent = systems["double_gauss"]
     table, aim = ent["tables"][0], ent["aim"][0][3]
     y0, u0 = aim_infinite(aim["field"], disc(n, 4), aim["z"], aim["p"], ent["object_angle"])
-    ref = eng.trace(table, y0, u0, clip=True, keep_last=True, want=("y",))[0][0]
-    off = 192
+    ref_y, _, ref_i, _ = eng.trace(table, y0, u0, clip=True, keep_last=True)
     npad = (off + n + 63)//64*64 + 64
     bufs = [eng.empty((npad, 3)) for _ in range(2)]
-    for b in bufs:
+    bufs_i = [eng.empty((npad, 3)) for _ in range(2)] if with_i else None
+    for b in bufs + (bufs_i or []):
         eng.lib.rtx_memset(eng.ctx, b.ptr, 0xff, b.nbytes)
     d_y0, d_u0 = eng.to_device(y0), eng.to_device(u0)
-    eng.trace_gather(table, d_y0, d_u0, [b.ptr for b in bufs], off, clip=True)
+    eng.trace_gather(table, d_y0, d_u0, [b.ptr for b in bufs], off, clip=True,
+                     dst_i_ptrs=[b.ptr for b in bufs_i] if with_i else None)
     eng.sync()
-    for b in bufs:
-        h = b.download()
-        assert np.array_equal(h[off:off + n], ref, equal_nan=True)
-        assert np.isnan(h[:off]).all()            # nothing written in front of the shard
-        b.free()
+    for group, ref in ((bufs, ref_y[0]), (bufs_i or [], ref_i[0])):
+        for b in group:
+            h = b.download()
+            assert np.array_equal(h[off:off + n], ref, equal_nan=True)
+            assert np.isnan(h[:off]).all()            # nothing written in front of the shard
+            assert np.isnan(h[off + n:]).all()        # ... nor behind it
+            b.free()
     d_y0.free()
     d_u0.free()
+
+
+def test_memory_helpers_and_numa(eng):
+    """rtx_memcpy_d2d, page-locked arrays that outlive their owner, and
+    rtx_numa_bind (bind + restore; a platform that reports no node is fine)"""
+    import gc
+    import os
+    a = np.arange(30, dtype=np.float64).reshape(10, 3)
+    d1, d2 = eng.to_device(a), eng.empty((10, 3))
+    d2.copy_from(d1)
+    assert np.array_equal(d2.download(), a)
+    assert np.array_equal(eng.download_rays(d2, np.arange(1, 10, 3)), a[1:10:3])
+    assert np.array_equal(eng.download_rays(d2, [7, 2, 2]), a[[7, 2, 2]])
+    p = eng.pinned_empty((4, 1000, 3))
+    p[:] = 3.
+    row = p[2]
+    del p
+    gc.collect()
+    assert row.sum() == 9000.                 # the view keeps the allocation alive
+    before = os.sched_getaffinity(0)
+    node = eng.numa_bind(True)
+    assert node >= -1 and len(os.sched_getaffinity(0)) >= 1
+    q = eng.pinned_empty((1000, 3))           # allocated under the binding
+    q[:] = 1.
+    eng.numa_bind(False)
+    assert os.sched_getaffinity(0) == before
+    assert q.sum() == 3000.
 
 
 def test_device_refocus_shift(eng):
