@@ -21,7 +21,8 @@ y,u,i,t stored).  Metric: ray-surface intersections per second.
   roofline  HBM: algorithmic bytes N*(6w + 10w*S) per launch / mean launch
             duration (CUDA events around every launch, separate pass)
   cpu_baseline  the REFERENCE itself (oracle/_ref, staged by oracle/make_ref.py)
-            on all host cores, bounded sample; numpy port as fallback
+            on all host cores: the whole workload ray-sharded over the cores;
+            numpy port as fallback
   headline  (N=1, when the HBM is free) the north-star point: zoom S=20,
             1e8 rays, FP64, full trace resident, one launch
   multi_gpu (N>1) C4: every rank traces 1.25e8 rays generated in HBM and the
@@ -31,8 +32,8 @@ y,u,i,t stored).  Metric: ray-surface intersections per second.
   parity_ok samples of the timed results checked against the oracle (asserted)
 
 `--impl reference` times the reference's own CPU path -- GeometricTrace.
-rays_given + propagate of quartiq/rayopt, ray-sharded over all host cores --
-on a bounded sample of the same workload per step (oracle/cpu_bench.py).
+rays_given + propagate of quartiq/rayopt -- on the same workload, ray-sharded
+over all host cores (oracle/cpu_bench.py; one step = 1e7 rays x 3 wavelengths).
 """
 import argparse
 import json
@@ -56,7 +57,6 @@ FIELD = (0., .7)
 N_RAYS = 10_000_000        # per wavelength
 WORKLOAD = ("C2: Double-Gauss 12-surface, 1e7 rays x 3 wavelengths, FP64, "
             "clip=True, field (0,0.7), full trace (y,u,i,t) stored")
-CPU_RAYS_PER_PROC = 400_000
 
 
 def load_system(name):
@@ -142,23 +142,27 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_reference(steps, warmup, rays_per_proc=CPU_RAYS_PER_PROC):
+def cpu_reference(steps, warmup):
     """The reference's CPU path on all host cores, in its own process
     (oracle/cpu_bench.py: no fork out of a CUDA process, no inherited NUMA
-    binding).  Returns cpu_bench's dict."""
+    binding): every step is the WHOLE C2 workload -- 1e7 rays per wavelength,
+    ray-sharded over os.cpu_count() processes (78 125 rays per process on a
+    128-thread host; with 4e5 rays per process the same host measured 3.0e7
+    ray-surfaces/s, profiles/r2a_bench.json, so the natural sharding is also
+    the reference's better case).  Returns cpu_bench's dict."""
     cmd = [sys.executable, os.path.join(ROOT, "oracle", "cpu_bench.py"), "--system", SYSTEM,
-           "--field", str(FIELD[0]), str(FIELD[1]), "--rays-per-proc", str(rays_per_proc),
+           "--field", str(FIELD[0]), str(FIELD[1]), "--rays-total", str(N_RAYS),
            "--steps", str(steps), "--warmup", str(warmup)]
     out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
     return json.loads(out.strip().splitlines()[-1])
 
 
 def cpu_sample_text(r):
-    return ("%d rays x %d wavelengths x %d surfaces per step (of 1e7 per wavelength): %d "
-            "processes x %d rays each, GeometricTrace.rays_given + propagate(clip=True), "
-            "%.1f s per step" % (r["rays_per_step_and_wavelength"], r["wavelengths"],
-                                 r["surfaces"], r["cores"], r["rays_per_proc"],
-                                 statistics.mean(r["seconds"])))
+    return ("the whole workload per step: %d rays x %d wavelengths x %d surfaces, ray-sharded over "
+            "%d processes x %d rays, quartiq/rayopt GeometricTrace.rays_given + "
+            "propagate(clip=True), %.1f s per step" % (
+                r["rays_per_step_and_wavelength"], r["wavelengths"], r["surfaces"], r["cores"],
+                r["rays_per_proc"], statistics.mean(r["seconds"])))
 
 
 def run_reference(args):
@@ -234,6 +238,12 @@ def leg_headline(eng, exact):
             "algorithmic_bytes": alg, "parity": par}
 
 
+def maxr_t(torch, dist, x):
+    t = torch.tensor([float(x)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def leg_c4(eng, dist, torch, exact, n_local=125_000_000):
     """C4: 1.25e8 rays per rank generated in HBM, trace + all-gather of y[-1]
     in one kernel per rank (TMA bulk stores into the IPC-mapped gather buffers
@@ -276,12 +286,32 @@ def leg_c4(eng, dist, torch, exact, n_local=125_000_000):
     want = np_oracle.trace(table, hy, hu, clip=True)[0][-1]
     got = eng.download_rays(pg.buf, pg.b[peer] + idx)
     par = check_sample(got, want, "peer segment")
-    ok = torch.tensor([1.0 if par["ok"] else 0.0], device="cuda")
+    # the statistics path: every rank reduces its shard INSIDE the
+    # trace kernel (rtx_trace_reduce, nothing stored), one NCCL all-reduce of 20
+    # doubles; checked against rtx_moments over the full gathered spot
+    center = np.zeros(4)
+    eng.trace_reduce(table, y0, u0, N=n_local, clip=True, exact=exact, center=center)
+    t0 = time.perf_counter()
+    m_loc = eng.trace_reduce(table, y0, u0, N=n_local, clip=True, exact=exact, center=center)
+    red_ms = eng.last_kernel_ms()
+    m = torch.tensor(m_loc, device="cuda")
+    dist.all_reduce(m, op=dist.ReduceOp.SUM)
+    m = m.cpu().numpy()
+    red_wall = maxr_t(torch, dist, (time.perf_counter() - t0)*1e3)
+    m_full = eng.moments(pg.buf, N=n_local*world, center=center[:2])
+    mom_err = float(np.max(np.abs(m[:8] - m_full)/np.maximum(np.abs(m_full), 1e-300)))
+    mom_ok = bool(m[5] == n_local*world and m[4] == m_full[4] and mom_err < 1e-11)
+    ok = torch.tensor([1.0 if (par["ok"] and mom_ok) else 0.0], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     pg.close()
     y0.free()
     u0.free()
-    return {"workload": "C4: Double-Gauss, %d rays per rank (%.3g total) generated in HBM, FP64, "
+    stats = {"api": "rtx_trace_reduce per rank + ONE NCCL all-reduce of 20 doubles",
+             "kernel_ms_this_rank": red_ms, "wall_ms_max_over_ranks": red_wall,
+             "rays_total": n_local*world, "rays_arrived": float(m[4]),
+             "vs_rtx_moments_of_gathered_spot_rel_err": mom_err, "ok": mom_ok}
+    return {"statistics_path": stats,
+            "workload": "C4: Double-Gauss, %d rays per rank (%.3g total) generated in HBM, FP64, "
                         "trace + gather of y[-1] to all %d ranks in one kernel per rank"
                         % (n_local, n_local*world, world),
             "kernel_ms_max_over_ranks": kms_max, "wall_ms_max_over_ranks": wall_max,

@@ -182,11 +182,12 @@ int64_t rtx_launch_count(rtx_ctx *ctx);
  *  keep     RTX_KEEP_ALL / RTX_KEEP_LAST
  *  ld       row pitch of the outputs in RAYS (>= N).  Outputs are DEVICE
  *           arrays Y,U,I: (rows, ld, 3), T: (rows, ld); rows = S or 1.
- *           With ld a multiple of 64 rays the kernel uses staged bulk (TMA)
- *           stores and writes whole 64-ray groups (columns N..ld-1 of the
- *           last group are padding and receive unspecified values); any
- *           other ld takes the per-thread store path and touches only
- *           columns < N.
+ *           With ld a multiple of 128 rays (64 suffices in FP64) the kernel
+ *           uses staged bulk (TMA) stores and writes whole groups of 32 x
+ *           rays-per-thread rays (columns N..ld-1 are padding and receive
+ *           unspecified values); a multiple of 32 or 64 selects a kernel with
+ *           fewer rays per thread; any other ld takes the per-thread store
+ *           path and touches only columns < N.
  *           Y: intercepts, U: excidence, I: incidence directions (unclipped),
  *           T: optical path s*n0 -- all in the surface-normal frame, exactly
  *           the tuple System.propagate yields (system.py:463).
@@ -264,11 +265,13 @@ int rtx_ipc_close(rtx_ctx *ctx, void *dptr);
  * collective.  dst_i (may be NULL) is a second set of npeers buffers that
  * receive the last surface's INCIDENCE directions i[-1] the same way (the
  * through-focus spots of rayopt/analysis.py:274-280 read y[-1] and i[-1]).
- * Bulk stores need dst_offset to be a multiple of 64 rays and write whole
- * 64-ray groups: with N a multiple of 64 exactly rays dst_offset ..
- * dst_offset + N - 1 are written; for any other N (or a misaligned offset /
- * buffer) the library falls back to per-ray stores that touch exactly N rays,
- * so a shard can never spill into its neighbour's range.  Asynchronous on
+ * Bulk stores need 16-byte aligned runs and write whole groups of 32 x
+ * rays-per-thread rays: with dst_offset and N multiples of 64 rays (FP64;
+ * 128 for the fastest FP32 kernel) exactly rays dst_offset .. dst_offset +
+ * N - 1 are written by bulk stores; for any other N or offset the library
+ * steps down to a kernel with smaller groups and finally to per-ray stores
+ * that touch exactly N rays, so a shard can never spill into its
+ * neighbour's range.  Asynchronous on
  * the context stream; after rtx_sync on every rank and a cross-rank barrier
  * all buffers hold the full spot.
  */
@@ -302,6 +305,55 @@ int rtx_selftest_math(rtx_ctx *ctx, int64_t n, const double *a, const double *b,
  */
 int rtx_moments(rtx_ctx *ctx, int dtype, int64_t N, const void *y,
                 const void *w, const double *center, double *m);
+
+/* ---- fused epilogues: the march with no per-surface stores */
+/*
+ * rms / centroid / refocus moments of surface S-1 in ONE launch from the
+ * launch rays (DEVICE y0,u0; surf[S] = system[start:at+1]): the trace kernel
+ * keeps the rays in registers, accumulates the moments there and writes 20
+ * doubles -- GeometricTrace.rms (rayopt/geometric_trace.py:171-183) and the
+ * focus shift of GeometricTrace.refocus (:82-99) of 1e9 rays without storing
+ * a single intercept.  About the guess centres center[0..1] (intercept x,y)
+ * and center[2..3] (slope i_x/i_z, i_y/i_z) -- e.g. the chief ray's, so that
+ * the shift to the true means is cancellation-free (host, 4 doubles or NULL);
+ * w: DEVICE weights (N values of dtype) or NULL (= 1).  m (host, 20 doubles):
+ *   m[0..7]   as rtx_moments (sum w, sum w dx, sum w dy, sum w (dx^2+dy^2),
+ *             #finite, #total, sum dx, sum dy)
+ *   m[8..19]  over the rays with a finite slope: #good, sum dy (2), sum du (2),
+ *             sum w, sum w dy (2), sum w du (2), sum w dy.du, sum w du.du
+ * Per-rank moments add up (one all-reduce of 20 doubles) for ray-sharded runs.
+ */
+#define RTX_NMOMENTS 20
+int rtx_trace_reduce(rtx_ctx *ctx, const rtx_surface *surf, int S,
+                     const double *rot0, int dtype, int64_t N, const void *y0,
+                     const void *u0, int clip, const void *w,
+                     const double *center, double *m, unsigned flags);
+
+/*
+ * The per-ray part of GeometricTrace.opd (rayopt/geometric_trace.py:101-131)
+ * as the epilogue of the march to surface `after` (surf[S] = system[1:after+1]):
+ *   A = sum_s t[s] - tj*n0 + ti*n_after,   P = y' + ti*u' - (0, 0, radius)
+ * with tj = u0_ref.(y0_ref - y0) for an object at infinity (`infinite`, :104-109),
+ * y' = y[after] @ M + d, u' = u[after] @ M the change to the image frame
+ * (:116-120; M = ea.rot_normal @ ei.rot_normal.T, d = (origins[after] -
+ * origins[image]) @ ei.rot_normal.T - y[image, ref]) and ti the intercept with
+ * the reference sphere Spheroid(curvature=1/radius) after y'_z += radius
+ * (:123-124).  The caller finishes with the reference ray:
+ *   t = -(A - A[ref])/(l/scale),  py = P - P[ref].
+ * A: DEVICE (N,), P: DEVICE (N,3) of dtype.  Asynchronous.
+ */
+typedef struct rtx_opd {
+    double y0_ref[3], u0_ref[3]; /* launch ray `ref` (row 0 of the trace) */
+    double n0, n_after;
+    double M[9], d[3];
+    double radius;
+    int32_t infinite;
+    int32_t reserved;
+} rtx_opd;
+int rtx_trace_opd(rtx_ctx *ctx, const rtx_surface *surf, int S,
+                  const double *rot0, int dtype, int64_t N, const void *y0,
+                  const void *u0, int clip, const rtx_opd *opd, void *A,
+                  void *P, unsigned flags);
 
 /* ---- launch rays generated in HBM -------------------------- */
 /*

@@ -5,7 +5,7 @@ TEST / BENCH INFRASTRUCTURE ONLY: used by bench.py's ``cpu_baseline`` and
 ``--impl reference`` legs, run as a separate process
 
     python oracle/cpu_bench.py --system double_gauss --field 0 0.7 \
-        --rays-per-proc 400000 --procs 128 --steps 20 --warmup 5
+        --rays-total 10000000 --steps 20 --warmup 5
 
 and prints one JSON line.  Nothing in the product imports it.
 
@@ -129,9 +129,14 @@ def reference_available():
 
 
 def run(system="double_gauss", field=(0., .7), rays_per_proc=400000, procs=None, steps=1,
-        warmup=1, kind=None, warm_rays=20000):
-    """-> dict(value ray-surfaces/s, kind, cores, seconds per timed step, ...)"""
+        warmup=1, kind=None, warm_rays=20000, rays_total=None):
+    """-> dict(value ray-surfaces/s, kind, cores, seconds per timed step, ...)
+    `rays_total`: shard a bundle of that many rays per wavelength over the
+    processes (rays_per_proc = ceil(rays_total/procs)) -- the actual workload,
+    ray-sharded over all cores, instead of a sample"""
     procs = procs or os.cpu_count() or 1
+    if rays_total:
+        rays_per_proc = -(-int(rays_total)//procs)
     if kind is None:
         kind = "reference" if reference_available() else "port"
     try:                                   # bound the resident set: ~1.3 kB per ray
@@ -188,13 +193,14 @@ def main():
     ap.add_argument("--system", default="double_gauss")
     ap.add_argument("--field", type=float, nargs=2, default=(0., .7))
     ap.add_argument("--rays-per-proc", type=int, default=400000)
+    ap.add_argument("--rays-total", type=int, default=0)
     ap.add_argument("--procs", type=int, default=0)
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--kind", default=None, choices=[None, "reference", "port"])
     a = ap.parse_args()
     print(json.dumps(run(a.system, a.field, a.rays_per_proc, a.procs or None, a.steps,
-                         a.warmup, a.kind)))
+                         a.warmup, a.kind, rays_total=a.rays_total or None)))
 
 
 if __name__ == "__main__":

@@ -63,6 +63,7 @@ struct rtx_ctx {
     size_t slot_bytes = 0;
     ChunkBuf chunk[2];
     double* d_moments = nullptr;
+    double* d_epi = nullptr;  // rtx_trace_reduce
     // small-bundle latency path (ray aiming: hundreds of 1-3 ray traces)
     void* small_host = nullptr;  // pinned: [y0|u0] in, [Y|U|I|T] out
     void* small_dev = nullptr;
@@ -192,8 +193,12 @@ int launch_cfg(rtx_ctx* ctx, const TraceParams<T>& p, int rpt, int store, int wa
     RTX_CASE(2, STORE_CTA, 16, 1)
     RTX_CASE(1, STORE_CTA, 16, 1)
     RTX_CASE(2, STORE_CTA, 32, 1)
-#ifdef RTX_TUNING_SPACE
     RTX_CASE(2, STORE_CTA, 8, 1)
+    if constexpr (sizeof(T) == 4) {  // FP32: four rays per thread (64 registers leave room)
+        RTX_CASE(4, STORE_CTA, 16, 1)
+        RTX_CASE(4, STORE_WARP, 8, 2)
+    }
+#ifdef RTX_TUNING_SPACE
     RTX_CASE(2, STORE_CTA, 8, 2)
     RTX_CASE(1, STORE_WARP, 16, 2)
     RTX_CASE(2, STORE_WARP, 8, 1)
@@ -203,6 +208,13 @@ int launch_cfg(rtx_ctx* ctx, const TraceParams<T>& p, int rpt, int store, int wa
     RTX_CASE(2, STORE_CTA, 16, 2)
     RTX_CASE(1, STORE_CTA, 32, 1)
     RTX_CASE(1, STORE_CTA, 32, 2)
+    if constexpr (sizeof(T) == 4) {
+        RTX_CASE(4, STORE_WARP, 8, 1)
+        RTX_CASE(4, STORE_CTA, 8, 1)
+        RTX_CASE(4, STORE_CTA, 32, 1)
+    }
+    RTX_CASE(2, STORE_WARP, 16, 2)
+    RTX_CASE(2, STORE_WARP, 16, 1)
 #endif
 #undef RTX_CASE
     return RTX_E_UNSUPPORTED;
@@ -342,25 +354,42 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
     if (flags & RTX_RPT2) rpt = 2;
     int store = ctx->store, warps = ctx->warps, nbuf = ctx->nbuf;
     bool heavy = false;
-    if (!ctx->tuned) {
-        // measured best configurations (profiles/r1_sweep8_defaults.txt):
-        //  FP64: 16 warps x 2 rays, per-CTA bulk stores (24 KB runs)      0.94
-        //  FP32: 32 warps x 2 rays (24 KB runs again)                     0.90
-        //  systems with >= 25 % Newton (aspheric) surfaces are bound by the
-        //  FP64/FP32 pipes and divergent iteration counts, not by HBM: small
-        //  8-warp CTAs, 2 rays per thread, per-warp stores and NO lockstep
-        //  (free-running warps hide the long dependent chains: 0.69 vs 0.60
-        //  in FP64, 0.63 vs 0.58 in FP32, profiles/r1_sweep12_asph_lockstep.txt)
+    const bool exact = (flags & RTX_EXACT) != 0;
+    const bool explicit_rpt = (flags & (RTX_RPT1 | RTX_RPT2)) != 0;
+    if (!ctx->tuned && !explicit_rpt) {
+        // measured best configurations (profiles/r1_sweep8_defaults.txt,
+        // r2b_sweep_newton_rewrite.txt; fractions of the measured HBM copy peak):
+        //  FP64: 2 rays/thread x 16 warps, per-CTA bulk stores (24 KB runs)      0.93-0.95
+        //  FP32: 4 rays/thread x 16 warps (2048-ray tiles, 24 KB runs again):
+        //        half the per-thread overhead instructions of 2 rays/thread     0.92-0.94
+        //  systems with >= 25 % Newton (aspheric) surfaces are bound by issue
+        //  slots / the FP64 pipe, not by HBM: small 8-warp CTAs (3 resident
+        //  CTAs per SM) -- FP64: per-CTA stores in lockstep 0.87; FP32: 4 rays
+        //  per thread, free-running warps with per-warp stores 0.85
         int newton = 0;
         for (int i = 0; i < S; ++i) newton += surf && surf[i].n_asph >= 0;
         heavy = newton * 4 >= S;
-        if (heavy && !(flags & (RTX_RPT1 | RTX_RPT2))) {
+        if (sizeof(T) == 4) {
+            rpt = 4;
+            if (heavy) {
+                store = STORE_WARP;
+                warps = 8;
+                nbuf = 2;
+            } else {
+                store = STORE_CTA;
+                warps = 16;
+                nbuf = 1;
+            }
+        } else if (heavy) {
             rpt = 2;
-            store = STORE_WARP;
             warps = 8;
-            nbuf = 2;
-        } else if (sizeof(T) == 4) {
-            warps = 32;
+            if (exact) {  // the separately rounded Newton keeps the free-running kernel
+                store = STORE_WARP;
+                nbuf = 2;
+            } else {
+                store = STORE_CTA;
+                nbuf = 1;
+            }
         }
     }
     if (N <= 32 * 1024) {  // small bundles: spread over more warps
@@ -368,27 +397,40 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
         store = STORE_WARP;
         warps = 8;
         nbuf = 2;
-    } else if ((flags & (RTX_RPT1 | RTX_RPT2))) {  // explicit RPT: its per-warp store kernel
+    } else if (explicit_rpt) {  // explicit RPT: its per-warp store kernel
         store = STORE_WARP;
         warps = 8;
         nbuf = 2;
     }
     const bool aligned = !(flags & RTX_STORE_DIRECT) && al16(Y) && al16(U) && al16(I) && al16(Tt) &&
                          peers_ok;
-    if (aligned && ld % (32 * rpt) != 0 && ld % 32 == 0) {
-        // a pitch of whole 32-ray groups only: the one-ray-per-thread
-        // per-warp bulk-store kernel still applies
-        rpt = 1;
-        store = STORE_WARP;
-        warps = 8;
-        nbuf = 2;
+    // The staged paths write whole 32*rpt-ray groups: the pitch must be a
+    // multiple of that, and so must the shard of a gather (into a gather buffer
+    // a ragged tail would spill clamped copies of the last ray into the next
+    // rank's range -- a race with that rank's own stores).
+    auto fits = [&](int r) { return ld % (32 * r) == 0 && (p.npeer == 0 || N % (32 * r) == 0); };
+    if (aligned && !ctx->tuned) {
+        // step down to the kernel with fewer rays per thread that fits
+        if (rpt == 4 && !fits(4)) {
+            rpt = 2;
+            if (heavy) {
+                store = STORE_WARP;
+                warps = 8;
+                nbuf = 2;
+            } else {
+                store = STORE_CTA;
+                warps = 32;
+                nbuf = 1;
+            }
+        }
+        if (rpt == 2 && !fits(2) && fits(1)) {
+            rpt = 1;
+            store = STORE_WARP;
+            warps = 8;
+            nbuf = 2;
+        }
     }
-    if (!(aligned && ld % (32 * rpt) == 0)) store = STORE_DIRECT;
-    // The staged paths write whole 32*rpt-ray groups.  Into a gather buffer
-    // that is only safe when the shard is a whole number of groups: a ragged
-    // tail would spill clamped copies of the last ray into the next rank's
-    // range (a race with that rank's own stores) -- per-ray stores instead.
-    if (p.npeer > 0 && N % (32 * rpt) != 0) store = STORE_DIRECT;
+    if (!(aligned && fits(rpt))) store = STORE_DIRECT;  // per-ray stores: exactly N rays
     if (batch && batch->n > 0) {
         p.nbatch = batch->n;
         for (int b = 0; b < batch->n; ++b) p.item[b] = batch->item[b];
@@ -522,12 +564,12 @@ int trace_host(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0,
             return trace_host_small<T>(ctx, surf, S, rot0, N, y0, u0, clip, keep, Y, U, I, Tt,
                                        flags, in_b, out_b);
     }
-    // chunk: ~256 MB of results, whole 64-ray groups
+    // chunk: ~256 MB of results, whole 128-ray groups
     long long per_ray = (long long)rows * 10 * sizeof(T) + 6 * sizeof(T);
     long long C = (256ll << 20) / per_ray;
-    C = (C / 64) * 64;
+    C = (C / 128) * 128;  // whole 128-ray groups: every staged kernel applies
     if (C < 4096) C = 4096;
-    if (C > N) C = ((N + 63) / 64) * 64;
+    if (C > N) C = ((N + 127) / 128) * 128;
     const size_t in_bytes = (size_t)C * 3 * sizeof(T);
     const size_t out3 = (size_t)rows * C * 3 * sizeof(T);
     const size_t out1 = (size_t)rows * C * sizeof(T);
@@ -666,7 +708,7 @@ int rtx_init(int device, rtx_ctx** out) {
     // tuning knobs (experiments; the defaults above are the measured best)
     if (const char* e = getenv("RTX_RPT")) {
         int v = atoi(e);
-        if (v == 1 || v == 2) ctx->default_rpt = v;
+        if (v == 1 || v == 2 || v == 4) ctx->default_rpt = v;
         ctx->tuned = true;
     }
     if (const char* e = getenv("RTX_WARPS")) {
@@ -702,6 +744,7 @@ int rtx_free(rtx_ctx* ctx) {
     free_chunk(ctx->chunk[0]);
     free_chunk(ctx->chunk[1]);
     if (ctx->d_moments) cudaFree(ctx->d_moments);
+    if (ctx->d_epi) cudaFree(ctx->d_epi);
     if (ctx->small_host) cudaFreeHost(ctx->small_host);
     if (ctx->small_dev) cudaFree(ctx->small_dev);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
@@ -1052,7 +1095,7 @@ int rtx_trace_gather(rtx_ctx* ctx, const rtx_surface* surf, int S, const double*
     }
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventRecord(ctx->k0, ctx->stream));
-    const long long ld = ((N + 63) / 64) * 64;  // only the gather destinations are written
+    const long long ld = ((N + 127) / 128) * 128;  // only the gather destinations are written
     if (dtype == RTX_F64)
         rc = trace_device<double>(ctx, surf, S, rot0, N, y0, u0, clip, RTX_KEEP_LAST, ld, nullptr,
                                   nullptr, nullptr, nullptr, flags, ctx->stream, nullptr, &pd);
@@ -1112,6 +1155,139 @@ int rtx_moments(rtx_ctx* ctx, int dtype, int64_t N, const void* y, const void* w
     }
     CK(cudaMemcpyAsync(m, ctx->d_moments, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"
+
+namespace {
+template <typename T, int MODE>
+int launch_epi(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0, long long N,
+               const void* y0, const void* u0, int clip, unsigned flags, EpiParams<T>& p) {
+    const DevSurf<T>* table = nullptr;
+    int rc = upload_table<T>(ctx, surf, S, ctx->stream, &table);
+    if (rc) return rc;
+    p.table = table;
+    p.S = S;
+    p.clip = clip ? 1 : 0;
+    p.has_rot0 = rot0 != nullptr;
+    if (rot0)
+        for (int i = 0; i < 9; ++i) p.rot0[i] = (T)rot0[i];
+    p.N = N;
+    p.y0 = (const T*)y0;
+    p.u0 = (const T*)u0;
+    const bool exact = (flags & RTX_EXACT) != 0;
+    if (exact && sizeof(T) == 4) return RTX_E_UNSUPPORTED;
+    constexpr int RPT = 2, threads = 256;
+    size_t smem = (((size_t)S * sizeof(DevSurf<T>) + 127) & ~size_t(127)) + 16;
+    if ((int)smem > ctx->max_smem_optin) return RTX_E_UNSUPPORTED;
+    auto go = [&](auto kern) -> int {
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+        if (occ < 1) occ = 1;
+        const long long tiles = (N + threads * RPT - 1) / (threads * RPT);
+        long long grid = (long long)ctx->sm_count * occ;
+        if (grid > tiles) grid = tiles;
+        if (grid < 1) grid = 1;
+        kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(p);
+        ctx->launches++;
+        return (int)cudaGetLastError();
+    };
+    if constexpr (sizeof(T) == 8) {
+        if (exact) return go(epi_kernel<T, true, RPT, MODE>);
+    }
+    return go(epi_kernel<T, false, RPT, MODE>);
+}
+}  // namespace
+
+extern "C" {
+
+int rtx_trace_reduce(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0, int dtype,
+                     int64_t N, const void* y0, const void* u0, int clip, const void* w,
+                     const double* center, double* m, unsigned flags) {
+    if (!ctx || !m) return RTX_E_BADARG;
+    int rc = check_table(surf, S);
+    if (rc) return rc;
+    if (N < 0 || !y0 || !u0) return RTX_E_BADARG;
+    if (dtype != RTX_F64 && dtype != RTX_F32) return RTX_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->d_epi) CK(cudaMalloc((void**)&ctx->d_epi, RTX_NMOMENTS * sizeof(double)));
+    CK(cudaMemsetAsync(ctx->d_epi, 0, RTX_NMOMENTS * sizeof(double), ctx->stream));
+    if (N > 0) {
+        CK(cudaEventRecord(ctx->k0, ctx->stream));
+        if (dtype == RTX_F64) {
+            EpiParams<double> p;
+            memset(&p, 0, sizeof(p));
+            p.w = (const double*)w;
+            for (int k = 0; k < 2; ++k) {
+                p.cy[k] = center ? center[k] : 0.0;
+                p.cu[k] = center ? center[2 + k] : 0.0;
+            }
+            p.out = ctx->d_epi;
+            rc = launch_epi<double, EPI_REDUCE>(ctx, surf, S, rot0, N, y0, u0, clip, flags, p);
+        } else {
+            EpiParams<float> p;
+            memset(&p, 0, sizeof(p));
+            p.w = (const float*)w;
+            for (int k = 0; k < 2; ++k) {
+                p.cy[k] = center ? center[k] : 0.0;
+                p.cu[k] = center ? center[2 + k] : 0.0;
+            }
+            p.out = ctx->d_epi;
+            rc = launch_epi<float, EPI_REDUCE>(ctx, surf, S, rot0, N, y0, u0, clip, flags, p);
+        }
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->k1, ctx->stream));
+        ctx->kernel_timed = true;
+    }
+    CK(cudaMemcpyAsync(m, ctx->d_epi, RTX_NMOMENTS * sizeof(double), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int rtx_trace_opd(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0, int dtype,
+                  int64_t N, const void* y0, const void* u0, int clip, const rtx_opd* opd, void* A,
+                  void* P, unsigned flags) {
+    if (!ctx || !opd || !A || !P) return RTX_E_BADARG;
+    int rc = check_table(surf, S);
+    if (rc) return rc;
+    if (N < 0 || !y0 || !u0 || opd->radius == 0.0) return RTX_E_BADARG;
+    if (dtype != RTX_F64 && dtype != RTX_F32) return RTX_E_BADARG;
+    if (N == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    auto fill = [&](auto& p) {
+        memset(&p, 0, sizeof(p));
+        p.infinite = opd->infinite;
+        for (int k = 0; k < 3; ++k) {
+            p.y0r[k] = opd->y0_ref[k];
+            p.u0r[k] = opd->u0_ref[k];
+            p.d[k] = opd->d[k];
+        }
+        for (int k = 0; k < 9; ++k) p.M[k] = opd->M[k];
+        p.n0 = opd->n0;
+        p.n_after = opd->n_after;
+        p.radius = opd->radius;
+    };
+    CK(cudaEventRecord(ctx->k0, ctx->stream));
+    if (dtype == RTX_F64) {
+        EpiParams<double> p;
+        fill(p);
+        p.A = (double*)A;
+        p.P = (double*)P;
+        rc = launch_epi<double, EPI_OPD>(ctx, surf, S, rot0, N, y0, u0, clip, flags, p);
+    } else {
+        EpiParams<float> p;
+        fill(p);
+        p.A = (float*)A;
+        p.P = (float*)P;
+        rc = launch_epi<float, EPI_OPD>(ctx, surf, S, rot0, N, y0, u0, clip, flags, p);
+    }
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->k1, ctx->stream));
+    ctx->kernel_timed = true;
     return 0;
 }
 

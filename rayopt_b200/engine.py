@@ -16,6 +16,11 @@ from .surface_table import SURFACE_DTYPE
 
 _DTYPES = {np.dtype(np.float64): RTX_F64, np.dtype(np.float32): RTX_F32}
 
+# mirrors `struct rtx_opd` (include/rtx.h)
+OPD_DTYPE = np.dtype([("y0_ref", "<f8", (3,)), ("u0_ref", "<f8", (3,)), ("n0", "<f8"),
+                      ("n_after", "<f8"), ("M", "<f8", (9,)), ("d", "<f8", (3,)),
+                      ("radius", "<f8"), ("infinite", "<i4"), ("reserved", "<i4")], align=True)
+
 
 def _code(dtype):
     try:
@@ -327,6 +332,74 @@ class Engine:
             self.ctx, ptr(table), len(table), ptr(r0), _code(y0.dtype), N, y0.ptr, u0.ptr,
             int(bool(clip)), len(dst_ptrs), C.cast(arr, C.c_void_p), arr_i, int(dst_offset),
             self._flags(exact, False)))
+
+    # ---- fused epilogues (no per-surface stores) -------------------------
+    def trace_reduce(self, table, y0, u0, N=None, clip=False, rot0=None, exact=False, w=None,
+                     center=None):
+        """rtx_trace_reduce: march the DEVICE launch rays to the last surface
+        of `table` and return the 20 rms / refocus moments of that surface
+        (include/rtx.h) -- one launch, no intercept is stored.  `center`:
+        (y_x, y_y, u_x, u_y) guess centres (e.g. the chief ray's)."""
+        table = self._table(table)
+        N = y0.shape[0] if N is None else int(N)
+        r0 = None if rot0 is None else np.ascontiguousarray(rot0, np.float64).reshape(9)
+        c = None if center is None else np.ascontiguousarray(center, np.float64).reshape(4)
+        m = np.zeros(20)
+        check(self.lib.rtx_trace_reduce(
+            self.ctx, ptr(table), len(table), ptr(r0), _code(y0.dtype), N, y0.ptr, u0.ptr,
+            int(bool(clip)), None if w is None else w.ptr, ptr(c), ptr(m),
+            self._flags(exact, False)))
+        return m
+
+    @staticmethod
+    def rms_from_moments(m, unit_weights=False, about_center=False):
+        """GeometricTrace.rms (rayopt/geometric_trace.py:171-183) from the
+        moments of ONE pass about a guess centre c: the spot is re-centred on
+        the unweighted mean analytically, sum w |y - ybar|^2 = m3 - 2 ybar.(m1,
+        m2) + |ybar|^2 m0 with ybar = (m6, m7)/N relative to c (cancellation
+        free when c is within the spot).  Not NaN-masked, like the reference.
+        `about_center`: rms about c itself (the reference's `ref` ray).
+        `unit_weights`: the moments were taken with w = 1 -> default 1/N."""
+        if m[4] != m[5] or m[5] == 0:
+            return float("nan")
+        if about_center:
+            r2 = m[3]
+        else:
+            bx, by = m[6]/m[5], m[7]/m[5]
+            r2 = m[3] - 2*(bx*m[1] + by*m[2]) + (bx*bx + by*by)*m[0]
+        if unit_weights:
+            r2 /= m[5]
+        return float(np.sqrt(max(r2, 0.)))
+
+    @staticmethod
+    def focus_shift_from_moments(m):
+        """the shift of GeometricTrace.refocus (rayopt/geometric_trace.py:82-99),
+        t = -<w dy, du>/<w du, du> about the unweighted means of the rays
+        with finite slope, from the one-pass sums m[8..19]"""
+        G = m[8]
+        if G == 0:
+            return float("nan")
+        by, bu = m[9:11]/G, m[11:13]/G
+        W, Wy, Wu = m[13], m[14:16], m[16:18]
+        num = m[18] - by.dot(Wu) - bu.dot(Wy) + by.dot(bu)*W
+        den = m[19] - 2*bu.dot(Wu) + bu.dot(bu)*W
+        return float(-num/den)
+
+    def trace_opd(self, table, y0, u0, spec, A, P, N=None, clip=False, rot0=None, exact=False):
+        """rtx_trace_opd: `spec` a dict with the members of `struct rtx_opd`
+        (include/rtx.h); A (N,), P (N,3) DeviceArrays.  Asynchronous."""
+        table = self._table(table)
+        N = y0.shape[0] if N is None else int(N)
+        r0 = None if rot0 is None else np.ascontiguousarray(rot0, np.float64).reshape(9)
+        rec = np.zeros(1, OPD_DTYPE)
+        for k in ("y0_ref", "u0_ref", "M", "d"):
+            rec[k] = np.asarray(spec[k], float).reshape(rec[k].shape[1:])
+        for k in ("n0", "n_after", "radius"):
+            rec[k] = float(spec[k])
+        rec["infinite"] = int(bool(spec["infinite"]))
+        check(self.lib.rtx_trace_opd(
+            self.ctx, ptr(table), len(table), ptr(r0), _code(y0.dtype), N, y0.ptr, u0.ptr,
+            int(bool(clip)), ptr(rec), A.ptr, P.ptr, self._flags(exact, False)))
 
     def ipc_export(self, darray):
         h = (C.c_ubyte*64)()

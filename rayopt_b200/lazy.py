@@ -140,6 +140,21 @@ class ResidentMixin:
     engine = None
     exact = False
     resident = True
+
+    # the reference's default weights ones(N)/N (geometric_trace.py:57-58) are
+    # materialised on first read: at 1e7 rays building them costs more than the
+    # trace, and the device reductions never need them (w = None means 1/N)
+    @property
+    def w(self):
+        if self._w is None and getattr(self, "_w_default", False):
+            self._w = np.ones(self.nrays)/self.nrays
+        return self._w
+
+    @w.setter
+    def w(self, value):
+        self._w = value
+        self._w_default = False
+    _w = None
     # i[j] == u[j-1] bit for bit in unrotated systems (system.py:461-463): u and
     # i are then two row-shifted views of ONE (S+2, ld, 3) device buffer and the
     # kernel stores 56 instead of 80 bytes per ray-surface
@@ -210,8 +225,8 @@ class ResidentMixin:
         if self._dev is None or self.nrays != count:
             self.allocate(count)
         self.l = self.system.wavelengths[0] if l is None else l
+        self.w = w
         self._w_default = w is None
-        self.w = np.ones(count)/count if w is None else w
         self._w_dev = None
         self.ref = ref
         if width != 3:
@@ -265,6 +280,7 @@ class ResidentMixin:
             None if self._i_alias else d["i"].rows(*sl), d["t"].rows(*sl),
             N=self.nrays, ld=self._ld, clip=clip, rot0=rot0, exact=self.exact)
         self.n[start:start + rows] = n
+        self._last_clip = bool(clip)
         touched = range(start, start + rows)
         for a in (self.y, self.u, self.t):
             a.invalidate(touched)
@@ -274,12 +290,12 @@ class ResidentMixin:
     # ---- reductions that never bring the rays to the host
     def _weights(self):
         """device copy of self.w, or None for the default 1/N weights"""
-        if self.w is None or getattr(self, "_w_default", False):
+        if self._w is None or getattr(self, "_w_default", False):
             return None
-        if self._w_dev is None or self._w_dev[0] is not self.w:
+        if self._w_dev is None or self._w_dev[0] is not self._w:
             if self._w_dev is not None:
                 self._w_dev[1].free()
-            self._w_dev = (self.w, self._engine().to_device(np.asarray(self.w, float)))
+            self._w_dev = (self._w, self._engine().to_device(np.asarray(self._w, float)))
         return self._w_dev[1]
 
     def rms(self, i=-1, ref=None):
@@ -301,6 +317,101 @@ class ResidentMixin:
                                   self._weights(), N=self.nrays)
         self.system[at].distance += shift
         self.propagate()
+
+
+    # ---- fused epilogues: the march itself reduces (no rows are stored or read)
+    def _guess_center(self, table, rot0, clip):
+        """(y_x, y_y, u_x, u_y) of the `ref` ray at the last surface of `table`
+        (a 1-ray trace through the small-bundle path), zeros if it dies"""
+        eng, d = self._engine(), self._dev
+        ref = 0 if self.ref is None else int(self.ref)
+        y0 = eng.download_rays(d["y"].rows(0), [ref])
+        u0 = eng.download_rays(d["u"].rows(0), [ref])
+        Y, _, I, _ = eng.trace(table, y0, u0, clip=clip, rot0=rot0, keep_last=True,
+                               exact=self.exact, want=("y", "i"))
+        c = np.r_[Y[0, 0, :2], I[0, 0, :2]/I[0, 0, 2]]
+        return c if np.all(np.isfinite(c)) else np.zeros(4)
+
+    def reduce(self, at=-1, clip=False):
+        """ONE launch from the launch rays (row 0) to surface `at`: the trace
+        kernel accumulates the rms / refocus moments of that surface in
+        registers (rtx_trace_reduce) and stores nothing else.  Returns the 20
+        moments (include/rtx.h) and the guess centre they refer to."""
+        at = range(self.length)[at]
+        table, _, rot0 = pack_system(self.system, self.l, 1, at + 1, n0=self.n[0])
+        c = self._guess_center(table, rot0, clip)
+        d = self._dev
+        m = self._engine().trace_reduce(table, d["y"].rows(0), d["u"].rows(0), N=self.nrays,
+                                        clip=clip, rot0=rot0, exact=self.exact,
+                                        w=self._weights(), center=c)
+        return m, c
+
+    def rms_fused(self, at=-1, clip=False):
+        """GeometricTrace.rms of surface `at` without a stored trace"""
+        m, _ = self.reduce(at, clip)
+        return self._engine().rms_from_moments(m, unit_weights=self._weights() is None)
+
+    def refocus_fused(self, at=-1, clip=False):
+        """GeometricTrace.refocus (geometric_trace.py:82-99) from one fused
+        launch: the focus shift is applied to ``system[at].distance`` and
+        returned; nothing is re-traced"""
+        m, _ = self.reduce(at, clip)
+        shift = self._engine().focus_shift_from_moments(m)
+        self.system[at].distance += shift
+        return shift
+
+    def opd_rays(self, radius=None, after=-2, image=-1):
+        """per-ray part of GeometricTrace.opd (rayopt/geometric_trace.py:
+        101-131) as the epilogue of a march from row 0 to surface `after`
+        (rtx_trace_opd); the reference ray's terms are subtracted here.
+        Returns (x, y, t): exit-pupil coordinates and the OPD in waves -- what
+        ``opd(resample=False)`` returns in the reference.  Needs a propagated
+        trace (the sphere is centred on ``y[image, ref]``)."""
+        eng, s, d = self._engine(), self.system, self._dev
+        after, image = range(self.length)[after], range(self.length)[image]
+        ref = int(self.ref)
+        if radius is None:                                  # :110-114
+            if s.image.pupil.telecentric:
+                radius = self.track[image] - self.track[after]
+            else:
+                radius = -s.image.pupil.distance
+        ea, ei = s[after], s[image]
+        eye = np.eye(3)
+        Ra = np.asarray(ea.rot_normal, float) if getattr(ea, "rotated", False) else eye
+        Ri = np.asarray(ei.rot_normal, float) if getattr(ei, "rotated", False) else eye
+        y_img_ref = eng.download_rays(d["y"].rows(image), [ref])[0]
+        spec = dict(y0_ref=eng.download_rays(d["y"].rows(0), [ref])[0],
+                    u0_ref=eng.download_rays(d["u"].rows(0), [ref])[0],
+                    n0=self.n[0], n_after=self.n[after], M=Ra @ Ri.T,
+                    d=(self.origins[after] - self.origins[image]) @ Ri.T - y_img_ref,
+                    radius=radius, infinite=not s.object.finite)
+        table, _, rot0 = pack_system(s, self.l, 1, after + 1, n0=self.n[0])
+        A, P = eng.empty((self.nrays,)), eng.empty((self.nrays, 3))
+        eng.trace_opd(table, d["y"].rows(0), d["u"].rows(0), spec, A, P, N=self.nrays,
+                      clip=getattr(self, "_last_clip", False), rot0=rot0, exact=self.exact)
+        a, p = A.download(), P.download()
+        A.free()
+        P.free()
+        t = -(a - a[ref])/(self.l/s.scale)                  # :125-126
+        p -= p[ref]                                         # :131
+        return p[:, 0], p[:, 1], t
+
+    def opd(self, radius=None, after=-2, image=-1, resample=4):
+        """GeometricTrace.opd with the per-ray part on the device; the
+        regridding (scipy griddata, geometric_trace.py:133-144) stays on the host"""
+        x, y, t = self.opd_rays(radius, after, image)
+        if resample:
+            from scipy.interpolate import griddata
+            ok = np.isfinite(x) & np.isfinite(y) & np.isfinite(t)
+            x, y, t = x[ok], y[ok], t[ok]
+            if not t.size:
+                raise ValueError("no rays made it through")
+            n = int(resample*self.nrays**.5)
+            h = np.fabs((x, y)).max()
+            xs, ys = np.mgrid[-1:1:1j*n, -1:1:1j*n]*h
+            t = griddata((x, y), t, (xs, ys), method="linear", fill_value=np.nan)
+            x, y = xs, ys
+        return x, y, t
 
 
 class ResidentTrace(ResidentMixin):
@@ -330,7 +441,7 @@ class ResidentTrace(ResidentMixin):
         if self._dev is None or self.nrays != count:
             self.allocate(count)
         self.l = self.system.wavelengths[0] if l is None else l
-        self.w = np.full(count, 1./count)
+        self.w = None
         self._w_default, self._w_dev = True, None
         self.ref = ref
         frame = np.concatenate(aim_frame(yo, z, angle))

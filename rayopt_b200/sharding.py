@@ -88,22 +88,57 @@ class LocalComm:
         pass
 
 
+def rms_from_moments(m, unit_weights=False):
+    """see Engine.rms_from_moments (pure numpy; kept importable without CUDA)"""
+    from .engine import Engine
+    return Engine.rms_from_moments(m, unit_weights)
+
+
 class ShardedTrace:
     """Trace a ray bundle sharded over ranks.
 
     `tracer(table, y0, u0, clip, keep_last)` -> (Y, U, I, T) host arrays for
     the LOCAL shard; by default the CUDA engine of this rank's GPU.
+    `reducer(table, y0, u0, clip, w, center)` -> the 20 moments of
+    rtx_trace_reduce for the LOCAL shard (host arrays in); by default the fused
+    CUDA epilogue (the shard is uploaded, no intercept is stored or read back).
     """
 
-    def __init__(self, comm=None, tracer=None, engine=None):
+    def __init__(self, comm=None, tracer=None, engine=None, reducer=None):
         self.comm = comm or LocalComm()
+        if (tracer is None or reducer is None) and engine is None:
+            from .engine import default_engine
+            engine = default_engine()
         if tracer is None:
-            if engine is None:
-                from .engine import default_engine
-                engine = default_engine()
             tracer = lambda t, y, u, clip, keep_last: engine.trace(  # noqa: E731
                 t, y, u, clip=clip, keep_last=keep_last)
+        if reducer is None:
+            def reducer(table, y, u, clip, w, center):
+                dy, du = engine.to_device(y), engine.to_device(u)
+                dw = None if w is None else engine.to_device(w)
+                try:
+                    return engine.trace_reduce(table, dy, du, clip=clip, w=dw, center=center)
+                finally:
+                    for a in (dy, du, dw):
+                        if a is not None:
+                            a.free()
         self.tracer = tracer
+        self.reducer = reducer
+
+    def moments(self, table, y0, u0, w=None, clip=False, center=None):
+        """the 20 rms / refocus moments (include/rtx.h rtx_trace_reduce) of the
+        WHOLE bundle: every rank reduces its shard inside the trace kernel, ONE
+        all-reduce of 20 doubles adds them up.  `center` must be
+        the same on every rank (e.g. the chief ray's intercept and slope)."""
+        wl = None if w is None else self.local(np.asarray(w, float))
+        m = self.reducer(table, self.local(y0), self.local(u0), clip, wl, center)
+        return self.comm.sum(m)
+
+    def rms_fused(self, table, y0, u0, w=None, clip=False, center=None):
+        """GeometricTrace.rms of the sharded bundle from one fused launch per
+        rank and one 160-byte all-reduce"""
+        m = self.moments(table, y0, u0, w, clip, center)
+        return rms_from_moments(m, unit_weights=w is None)
 
     def local(self, a):
         return shard(a, self.comm.rank, self.comm.world)

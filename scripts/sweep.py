@@ -18,16 +18,24 @@ ap.add_argument("--rays", type=int, default=10_000_000)
 ap.add_argument("--exact", type=int, default=0)
 ap.add_argument("--system", default="double_gauss")
 ap.add_argument("--dtype", default="f64")
+ap.add_argument("--device-rays", type=int, default=0,
+                help="1: hexapolar launch rays generated in HBM (large bundles)")
 ap.add_argument("cfgs", nargs="*", default=["2,2,16,1,0,0,1"])
 a = ap.parse_args()
 ent = bench.load_system(a.system)
 S, N = ent["S"], a.rays
 dt = np.float64 if a.dtype == "f64" else np.float32
 w = np.dtype(dt).itemsize
-ld = ((N + 63)//64)*64
 mem = Engine(0)
-y0, u0 = bench.make_rays(ent, 0, N, 0)
-d_y0, d_u0 = mem.to_device(y0, dt), mem.to_device(u0, dt)
+if a.device_rays:
+    aim = ent["aim"][0][bench.FIELD_INDEX]
+    d_y0, d_u0 = mem.aim_infinite_device(aim["field"], aim["z"], aim["p"], ent["object_angle"],
+                                         nrays=N, dtype=dt)
+    N = d_y0.shape[0]//128*128
+else:
+    y0, u0 = bench.make_rays(ent, 0, N, 0)
+    d_y0, d_u0 = mem.to_device(y0, dt), mem.to_device(u0, dt)
+ld = ((N + 127)//128)*128
 Y, U, I = (mem.empty((S, ld, 3), dt) for _ in range(3))
 T = mem.empty((S, ld), dt)
 alg = N*(6*w + 10*w*S)

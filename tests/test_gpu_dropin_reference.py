@@ -123,11 +123,62 @@ def test_refocus_rms_opd_of_the_reference_class_on_cuda(R, eng, resident):
     assert abs(got.rms(ref=0) - ref.rms(ref=0)) < 1e-13
     assert abs(got.rms(3) - ref.rms(3)) < 1e-12
     xr, yr, tr = ref.opd(resample=False)
-    xg, yg, tg = got.opd(resample=False)
+    xg, yg, tg = got.opd(resample=False)       # resident: the device epilogue rtx_trace_opd
     np.testing.assert_allclose(tg, tr, rtol=0, atol=1e-9)  # waves
     np.testing.assert_allclose(xg, xr, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(yg, yr, rtol=0, atol=1e-12)
+    xr, yr, tr = ref.opd()
+    xg, yg, tg = got.opd()
+    assert np.array_equal(np.isnan(tg), np.isnan(tr))
+    np.testing.assert_allclose(np.nan_to_num(tg), np.nan_to_num(tr), rtol=0, atol=1e-8)
     if resident:
+        # fused epilogues: one launch from row 0, nothing stored or read back
+        assert abs(got.rms_fused() - ref.rms()) < 1e-13
+        assert abs(got.rms_fused(3) - ref.rms(3)) < 1e-12
+        for t in (ref, got):
+            t.rays_point((0, .7), **kw)
+        d1, d2 = s1[-1].distance, s2[-1].distance
+        shift = got.refocus_fused(clip=True)
+        ref.refocus()
+        assert abs(shift - (s1[-1].distance - d1)) < 1e-11 and s2[-1].distance == d2 + shift
         got.free()
+
+
+def test_fused_reduce_large_bundle(R, eng):
+    """rtx_trace_reduce on a 3e5-ray aimed bundle: rms / centroid / vignetting
+    count / focus shift from ONE launch equal the reference's numbers computed
+    from its stored trace"""
+    from rayopt_b200 import bind
+    s = build(R, "double_gauss", defocus=.2)
+    n = 300001
+    rng = np.random.default_rng(11)
+    r, phi = np.sqrt(rng.random(n)), 2*np.pi*rng.random(n)
+    yp = np.c_[r*np.cos(phi), r*np.sin(phi)]
+    yp[0] = 0
+    w = rng.random(n)
+    w /= w.sum()
+    ref = R.GeometricTrace(s)
+    got = bind(R.GeometricTrace, engine=eng, resident=True)(s)
+    for t in (ref, got):
+        t.rays((0, .7), yp, s.wavelengths[1], clip=True, filter=False, weight=w)
+    m, c = got.reduce(clip=True)
+    good = np.isfinite(ref.y[-1, :, 0])
+    assert m[5] == n and m[4] == good.sum() and 0 < good.sum() < n
+    y = ref.y[-1, good, :2]
+    np.testing.assert_allclose(c[:2] + m[6:8]/m[4], y.mean(0), rtol=1e-13)
+    np.testing.assert_allclose(m[0], w[good].sum(), rtol=1e-12)
+    u = R.utils.tanarcsin(ref.i[-1])
+    ok = np.all(np.isfinite(u), axis=1)
+    yy, uu, ww = ref.y[-1, ok, :2], u[ok], w[ok]
+    yy, uu = yy - yy.mean(0), uu - uu.mean(0)
+    want = -np.dot((ww[:, None]*yy).ravel(), uu.ravel())/np.dot((ww[:, None]*uu).ravel(), uu.ravel())
+    assert abs(eng.focus_shift_from_moments(m) - want) < 1e-10*abs(want)
+    # rms needs an unvignetted bundle (the reference's rms is not NaN-masked)
+    for t in (ref, got):
+        t.rays((0, 0.), yp[:100000], s.wavelengths[0], clip=True, filter=False)
+    assert abs(got.rms_fused(clip=True) - ref.rms()) < 1e-12*ref.rms() + 1e-15
+    assert abs(got.rms_fused(5, clip=True) - ref.rms(5)) < 1e-12*ref.rms(5)
+    got.free()
 
 
 def test_analysis_consumers_read_single_rows(R, eng):

@@ -75,26 +75,69 @@ def test_fast_mode_vs_reference_golden(eng, name, rpt):
     _cmp(got, c, FP64_RTOL, "fast")
 
 
+def _fp32_err(a, b):
+    """SURVEY 8(d) comparator on the entries finite in both: max of
+    |a-b| / max(|b|, scale), scale = max finite |b| of the surface's array for
+    lengths (floor 1: direction cosines); returns (error, #NaN-mask flips)"""
+    a = np.asarray(a, np.float64)
+    flips = int((np.isnan(a) != np.isnan(b)).sum())
+    fin = ~np.isnan(a) & ~np.isnan(b)
+    absb = np.where(np.isnan(b), 0, np.abs(b))
+    scale = np.maximum(absb.reshape(len(b), -1).max(1), 1.0).reshape((-1,) + (1,)*(b.ndim - 1))
+    with np.errstate(invalid="ignore"):
+        e = np.where(fin, np.abs(a - b)/np.maximum(np.abs(np.where(fin, b, 1)), scale), 0)
+    return float(e.max()), flips
+
+
+# goldens built to sit ON a numerical edge (Newton at the limit of convergence;
+# total internal reflection / aperture edges of steep conics): in single
+# precision the NaN mask legitimately depends on the last bit
+FP32_EDGE = ("newton_edge", "conics")
+
+
 @pytest.mark.parametrize("name", golden_names())
 def test_fp32_vs_reference_golden(eng, name):
+    """FP32 kernels against the FP64 reference with the per-surface comparator
+    of SURVEY 8(d) at north_star's 1e-5.  Where single precision itself cannot
+    hold 1e-5 -- the on-axis image spot after 20 refractions (zoom_f0: the
+    direction error ~1.3e-6 times the 19 mm to the image), Newton at the edge
+    of convergence -- the bound is what a float32 numpy evaluation of the
+    REFERENCE'S OWN formulas (oracle/np_oracle.py, dtype=float32) achieves on
+    the same rays, times 1.5.  Measured per array: profiles/r2a_fp32_budget.txt
+    (real lenses 1e-7 .. 2.6e-6; zoom_f0 y 1.05e-5 vs numpy-f32 0.93e-5)."""
     c = load_golden(name)
-    if name.startswith(("newton_edge", "conics", "parabola")):
-        pytest.skip("ill-conditioned edge cases: NaN mask is precision dependent")
     got = eng.trace(c["table"], c["y0"], c["u0"], clip=c["clip"], rot0=c["rot0"],
                     dtype=np.float32)
-    # rays within FP32 resolution of an aperture edge / TIR may flip: compare
-    # where both are finite, and bound the number of mask flips
-    flips = 0
-    for a, b, w in zip(got, (c["Y"], c["U"], c["I"], c["T"]), "yuit"):
-        a = a.astype(np.float64)
-        m = np.isnan(a) != np.isnan(b)
-        flips = max(flips, int(m.sum()))
-        a = np.where(m, b, a)
-        # relative to the size of the lens (largest |value| of the whole
-        # trace): after 20 FP32 refractions an on-axis spot cannot be known to
-        # 1e-5 of its own (tiny) size
-        assert_parity(a, b, FP32_RTOL, "%s fp32 %s" % (name, w), global_scale=True)
-    assert flips <= max(2, c["y0"].shape[0]//100)*3*len(c["table"]), flips
+    f32 = np_oracle.trace(c["table"], c["y0"], c["u0"], clip=c["clip"], rot0=c["rot0"],
+                          dtype=np.float32)
+    edge = name.startswith(FP32_EDGE)
+    for a, o, b, w in zip(got, f32, (c["Y"], c["U"], c["I"], c["T"]), "yuit"):
+        err, flips = _fp32_err(a, b)
+        err_np, flips_np = _fp32_err(o, b)
+        if edge:
+            # mask-aware: the engine may flip no more rays than the reference's
+            # formulas in float32 do, and stays within 2e-5 where both are finite
+            assert flips <= max(flips_np, 3*len(c["table"])), (name, w, flips, flips_np)
+            assert err <= max(2e-5, 1.5*err_np), (name, w, err, err_np)
+        else:
+            assert flips == 0, "%s fp32 %s: NaN mask differs at %d entries" % (name, w, flips)
+            assert err <= max(FP32_RTOL, 1.5*err_np), "%s fp32 %s: %.2e (numpy float32 %.2e)" % (
+                name, w, err, err_np)
+
+
+@pytest.mark.parametrize("sysname", ["double_gauss", "cooke", "cooke_asph", "zoom"])
+def test_fp32_large_bundles(eng, systems, sysname):
+    """2e5-ray aimed bundles, FP32, per-surface comparator at 1e-5; rays within
+    FP32 resolution of an aperture edge may flip (< 0.1 % of the entries)"""
+    ent = systems[sysname]
+    aim = ent["aim"][0][3]
+    y0, u0 = aim_infinite(aim["field"], disc(200000, 9), aim["z"], aim["p"], ent["object_angle"])
+    want = np_oracle.trace(ent["tables"][0], y0, u0, clip=True)
+    got = eng.trace(ent["tables"][0], y0, u0, clip=True, dtype=np.float32)
+    for a, b, w in zip(got, want, "yuit"):
+        err, flips = _fp32_err(a, b)
+        assert flips <= 1e-3*b.size, (sysname, w, flips)
+        assert err <= FP32_RTOL, "%s fp32 %s: %.2e" % (sysname, w, err)
 
 
 def test_store_paths_identical_large(eng, systems):

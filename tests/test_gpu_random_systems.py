@@ -175,8 +175,11 @@ def test_random_general_systems(eng, seed):
             assert_parity(a, b, rtol, "seed %d exact=%s %s" % (seed, exact, w))
     # FP32 on random wild systems: the error is (condition number) x (FP32
     # rounding accumulated over ~100 operations per surface); rays with an
-    # amplification below 30 stay within 1e-4 of the lens size.  The 1e-5 bar
-    # is asserted on the real lens prescriptions (tests/test_gpu_parity.py).
+    # amplification below 30 stay within 1e-4 of the lens size -- that is the
+    # MEASURED bound for these synthetic prescriptions (tilted steep aspheres
+    # at random), stated as such.  north_star's 1e-5 with the per-surface
+    # comparator is asserted on the real lens prescriptions
+    # (tests/test_gpu_parity.py::test_fp32_vs_reference_golden, _large_bundles).
     ok32 = (well_conditioned(table, y0, u0, want, clip, rot0, amp=30) &
             reference_accurate(table, y0, u0, want, clip, rot0, tol=1e-13))
     got = eng.trace(table, y0, u0, clip=clip, rot0=rot0, dtype=np.float32)
