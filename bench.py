@@ -500,7 +500,7 @@ def main():
     # DRAM traffic per launch is NOT measurable from inside the process (it
     # needs ncu): the number below is carried over from the committed ncu
     # capture of this kernel at this size and labelled as such
-    traffic = 10_017_000_000 if (N == N_RAYS and not args.direct) else None
+    traffic = 10_017_400_000 if (N == N_RAYS and not args.direct) else None
 
     # ---- parity of the timed device-resident results (sample vs the oracle)
     idx = np.arange(0, N, max(1, N//2000))[:2000]
@@ -643,7 +643,7 @@ def main():
                          "frac": achieved/peak, "traffic": traffic,
                          "traffic_source": "from profile, not measured in this run: ncu "
                                            "dram__bytes_read.sum+dram__bytes_write.sum per launch of "
-                                           "this kernel at this size, profiles/r1_v8_dram_bytes_full_size.csv",
+                                           "this kernel at this size, profiles/r2c_dram_bytes_full_size.csv",
                          "peak_source": peak_src,
                          "kernel": "rtx::trace_kernel<double>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg_bytes},

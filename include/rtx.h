@@ -113,8 +113,11 @@ typedef struct rtx_ctx rtx_ctx;
 
 /* ---- library ---------------------------------------------------------- */
 int rtx_abi_version(void);
-/* sizeof(rtx_surface) as compiled, for binding-side layout checks */
+/* sizeof(rtx_surface) / sizeof(rtx_aim) / sizeof(rtx_opd) as compiled, for
+ * binding-side layout checks */
 size_t rtx_sizeof_surface(void);
+size_t rtx_sizeof_aim(void);
+size_t rtx_sizeof_opd(void);
 /* number of CUDA devices visible, or 0 */
 int rtx_device_count(void);
 /* static string for an rtx (negative) or CUDA (positive) error code */
@@ -380,6 +383,58 @@ int rtx_aim_infinite(rtx_ctx *ctx, int dtype, int64_t N, const void *yp,
 int rtx_aim_finite(rtx_ctx *ctx, int dtype, int64_t N, const void *yp,
                    int hex_rings, const double *frame, double am, double z,
                    void *y0, void *u0);
+
+/*
+ * General generator: the pupil grids of pupil_distribution (rayopt/utils.py:
+ * 118-199), Pupil.map with its elliptical filter (rayopt/pupils.py:97-107) and
+ * Conjugate.aim (rayopt/conjugates.py:137-166, 236-255) evaluated per ray on
+ * the device.  Candidates rejected by a predicate (mesh points outside the
+ * unit circle, rays outside the filter ellipse) are squeezed out in order
+ * (two passes: block counts, host prefix sum, generation).
+ *
+ *  conjugate  0 infinite: frame = {u[3], ybase[3] = yz - z*u, s[3], m[3]}
+ *             1 finite:   frame = {y[3] object point, u0[3], s[3], m[3]}
+ *             (the projection, a telecentric pupil and a curved FINITE object
+ *             surface only change these per-field constants: the host computes
+ *             them with the reference's expressions, rayopt_b200/rays.py)
+ *  grid       RTX_GRID_*; n = rings (hexapolar), mesh side (square,
+ *             triangular: n x n points clipped to the unit circle + centre
+ *             ray), number of random rays (+ centre ray); RTX_GRID_LINES: up to
+ *             two np.linspace segments seg[k] = (x0, y0, x1, y1) of seg_m[k]
+ *             points (meridional, sagittal, cross, tee, half-meridional);
+ *             RTX_GRID_GIVEN: pupil coordinates yp, DEVICE (n_given, 2) FP64
+ *  pmax       Pupil.map's scale fabs(a).max() (finite: of arctan2(a, z))
+ *  filter     keep ((q - fc)^2 / fd2).sum() <= 1, q the scaled coordinates
+ *  curved     infinite object only: intercept the rays with `surface`
+ *             (system[0], in its own frame) instead of the plane z = 0
+ */
+#define RTX_GRID_GIVEN      0
+#define RTX_GRID_HEXAPOLAR  1
+#define RTX_GRID_SQUARE     2
+#define RTX_GRID_TRIANGULAR 3
+#define RTX_GRID_RANDOM     4
+#define RTX_GRID_LINES      5
+typedef struct rtx_aim {
+    int32_t conjugate, grid, filter, curved;
+    int64_t n;
+    uint64_t seed;      /* RTX_GRID_RANDOM: counter-based generator */
+    double seg[2][4];
+    int64_t seg_m[2];
+    double frame[12];
+    double pmax, z;
+    double fc[2], fd2[2];
+    rtx_surface surface;
+} rtx_aim;
+/* number of rays the spec generates (runs the counting pass when a predicate
+ * can reject candidates; the plan is cached in the context) */
+int rtx_aim_plan(rtx_ctx *ctx, const rtx_aim *spec, int64_t n_given,
+                 const void *yp, int64_t *n_rays);
+/* rays first .. first+count-1 of the bundle into DEVICE y0,u0 (count,3) of
+ * dtype; yp_out: optional DEVICE (count,2) FP64 receiving the fractional pupil
+ * coordinates of those rays.  Asynchronous on the context stream. */
+int rtx_aim_rays(rtx_ctx *ctx, const rtx_aim *spec, int64_t n_given,
+                 const void *yp, int dtype, int64_t first, int64_t count,
+                 void *y0, void *u0, void *yp_out);
 
 /*
  * Moments for GeometricTrace.refocus (rayopt/geometric_trace.py:82-99) on

@@ -20,6 +20,8 @@ _pp = C.POINTER(C.c_void_p)
 SYMBOLS = {
     "rtx_abi_version": (_i, []),
     "rtx_sizeof_surface": (_sz, []),
+    "rtx_sizeof_aim": (_sz, []),
+    "rtx_sizeof_opd": (_sz, []),
     "rtx_device_count": (_i, []),
     "rtx_strerror": (C.c_char_p, [_i]),
     "rtx_surface_finalize": (_i, [_vp, _i, _vp]),
@@ -56,6 +58,8 @@ SYMBOLS = {
     "rtx_selftest_math": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "rtx_aim_infinite": (_i, [_vp, _i, _i64, _vp, _i, _vp, C.c_double, _vp, _vp]),
     "rtx_aim_finite": (_i, [_vp, _i, _i64, _vp, _i, _vp, C.c_double, C.c_double, _vp, _vp]),
+    "rtx_aim_plan": (_i, [_vp, _vp, _i64, _vp, C.POINTER(_i64)]),
+    "rtx_aim_rays": (_i, [_vp, _vp, _i64, _vp, _i, _i64, _i64, _vp, _vp, _vp]),
     "rtx_focus_moments": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "rtx_ipc_export": (_i, [_vp, _vp, _vp]),
     "rtx_ipc_open": (_i, [_vp, _vp, _pp]),
@@ -88,6 +92,10 @@ def load():
     if lib.rtx_sizeof_surface() != SURFACE_DTYPE.itemsize:
         raise RtxError("rtx_surface layout mismatch: C %d, numpy %d" % (
             lib.rtx_sizeof_surface(), SURFACE_DTYPE.itemsize))
+    from .rays import aim_dtype
+    if lib.rtx_sizeof_aim() != aim_dtype().itemsize:
+        raise RtxError("rtx_aim layout mismatch: C %d, numpy %d" % (
+            lib.rtx_sizeof_aim(), aim_dtype().itemsize))
     _lib = lib
     return lib
 

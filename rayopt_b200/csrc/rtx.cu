@@ -64,6 +64,12 @@ struct rtx_ctx {
     ChunkBuf chunk[2];
     double* d_moments = nullptr;
     double* d_epi = nullptr;  // rtx_trace_reduce
+    // cached plan of the ray generator (rtx_aim_plan / rtx_aim_rays)
+    std::vector<unsigned char> aim_key;
+    std::vector<long long> aim_offsets;  // per block; empty: nothing is rejected
+    long long* d_aim_offsets = nullptr;
+    size_t d_aim_cap = 0;
+    long long aim_total = 0, aim_M = 0;
     // small-bundle latency path (ray aiming: hundreds of 1-3 ray traces)
     void* small_host = nullptr;  // pinned: [y0|u0] in, [Y|U|I|T] out
     void* small_dev = nullptr;
@@ -645,6 +651,8 @@ extern "C" {
 int rtx_abi_version(void) { return RTX_ABI_VERSION; }
 
 size_t rtx_sizeof_surface(void) { return sizeof(rtx_surface); }
+size_t rtx_sizeof_aim(void) { return sizeof(rtx_aim); }
+size_t rtx_sizeof_opd(void) { return sizeof(rtx_opd); }
 
 int rtx_device_count(void) {
     int n = 0;
@@ -745,6 +753,7 @@ int rtx_free(rtx_ctx* ctx) {
     free_chunk(ctx->chunk[1]);
     if (ctx->d_moments) cudaFree(ctx->d_moments);
     if (ctx->d_epi) cudaFree(ctx->d_epi);
+    if (ctx->d_aim_offsets) cudaFree(ctx->d_aim_offsets);
     if (ctx->small_host) cudaFreeHost(ctx->small_host);
     if (ctx->small_dev) cudaFree(ctx->small_dev);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
@@ -1335,6 +1344,156 @@ int rtx_aim_finite(rtx_ctx* ctx, int dtype, int64_t N, const void* yp, int hex_r
             f[8], f[9], f[10], f[11], (float*)y0, (float*)u0);
     else
         return RTX_E_BADARG;
+    ctx->launches++;
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"
+
+namespace {
+int aim_to_dev(const rtx_aim* a, long long n_given, AimDev& d) {
+    memset(&d, 0, sizeof(d));
+    d.conjugate = a->conjugate;
+    d.grid = a->grid;
+    d.filter = a->filter;
+    d.curved = a->curved && a->conjugate == 0;
+    d.n = a->n;
+    d.seed = a->seed;
+    memcpy(d.seg, a->seg, sizeof(d.seg));
+    d.seg_m[0] = a->seg_m[0];
+    d.seg_m[1] = a->seg_m[1];
+    memcpy(d.frame, a->frame, sizeof(d.frame));
+    d.pmax = a->pmax;
+    d.z = a->z;
+    for (int k = 0; k < 2; ++k) {
+        d.fc[k] = a->fc[k];
+        d.fd2[k] = a->fd2[k];
+    }
+    if (d.curved) {
+        if (a->surface.n_asph > RTX_MAX_ASPH) return RTX_E_UNSUPPORTED;
+        convert_surface<double>(a->surface, d.surf);
+    }
+    switch (a->grid) {
+        case GRID_GIVEN: d.M = n_given; break;
+        case GRID_HEXAPOLAR: d.M = 1 + 3 * a->n * (a->n + 1); break;
+        case GRID_SQUARE:
+        case GRID_TRIANGULAR:
+            if (a->n < 2) return RTX_E_BADARG;
+            d.M = 1 + a->n * a->n;
+            break;
+        case GRID_RANDOM: d.M = 1 + a->n; break;
+        case GRID_LINES: d.M = a->seg_m[0] + a->seg_m[1]; break;
+        default: return RTX_E_BADARG;
+    }
+    if (a->n < 0 || d.M < 0 || a->seg_m[0] < 0 || a->seg_m[1] < 0) return RTX_E_BADARG;
+    if (a->conjugate != 0 && a->conjugate != 1) return RTX_E_BADARG;
+    return 0;
+}
+
+// counting pass + prefix sum, cached per (spec, n_given, yp)
+int aim_plan(rtx_ctx* ctx, const rtx_aim* spec, long long n_given, const void* yp, AimDev& d) {
+    int rc = aim_to_dev(spec, n_given, d);
+    if (rc) return rc;
+    if (spec->grid == GRID_GIVEN && n_given > 0 && !yp) return RTX_E_BADARG;
+    std::vector<unsigned char> key(sizeof(rtx_aim) + sizeof(long long) + sizeof(void*));
+    memcpy(key.data(), spec, sizeof(rtx_aim));
+    memcpy(key.data() + sizeof(rtx_aim), &n_given, sizeof(long long));
+    memcpy(key.data() + sizeof(rtx_aim) + sizeof(long long), &yp, sizeof(void*));
+    const bool rejects = spec->filter || spec->grid == GRID_SQUARE || spec->grid == GRID_TRIANGULAR;
+    // (a GIVEN grid may have changed behind the same pointer: always recount it)
+    if (key == ctx->aim_key && !(rejects && spec->grid == GRID_GIVEN)) return 0;
+    ctx->aim_key.clear();
+    ctx->aim_offsets.clear();
+    ctx->aim_M = d.M;
+    ctx->aim_total = d.M;
+    if (rejects && d.M > 0) {
+        const long long nb = (d.M + AIM_BLOCK - 1) / AIM_BLOCK;
+        if ((size_t)(nb + 1) * sizeof(long long) > ctx->d_aim_cap) {
+            if (ctx->d_aim_offsets) CK(cudaFree(ctx->d_aim_offsets));
+            ctx->d_aim_offsets = nullptr;
+            ctx->d_aim_cap = 0;
+            CK(cudaMalloc((void**)&ctx->d_aim_offsets, (size_t)(nb + 1) * sizeof(long long)));
+            ctx->d_aim_cap = (size_t)(nb + 1) * sizeof(long long);
+        }
+        int* d_counts = reinterpret_cast<int*>(ctx->d_aim_offsets);  // reused before the offsets
+        long long grid = nb < (long long)ctx->sm_count * 8 ? nb : (long long)ctx->sm_count * 8;
+        aim_count_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(d, (const double*)yp, d_counts, nb);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        std::vector<int> counts((size_t)nb);
+        CK(cudaMemcpyAsync(counts.data(), d_counts, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->aim_offsets.resize((size_t)nb + 1);
+        long long acc = 0;
+        for (long long b = 0; b < nb; ++b) {
+            ctx->aim_offsets[(size_t)b] = acc;
+            acc += counts[(size_t)b];
+        }
+        ctx->aim_offsets[(size_t)nb] = acc;
+        ctx->aim_total = acc;
+        CK(cudaMemcpyAsync(ctx->d_aim_offsets, ctx->aim_offsets.data(),
+                           (size_t)(nb + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->aim_key = key;
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int rtx_aim_plan(rtx_ctx* ctx, const rtx_aim* spec, int64_t n_given, const void* yp,
+                 int64_t* n_rays) {
+    if (!ctx || !spec || !n_rays || n_given < 0) return RTX_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    AimDev d;
+    int rc = aim_plan(ctx, spec, n_given, yp, d);
+    if (rc) return rc;
+    *n_rays = ctx->aim_total;
+    return 0;
+}
+
+int rtx_aim_rays(rtx_ctx* ctx, const rtx_aim* spec, int64_t n_given, const void* yp, int dtype,
+                 int64_t first, int64_t count, void* y0, void* u0, void* yp_out) {
+    if (!ctx || !spec || !y0 || !u0 || n_given < 0 || first < 0 || count < 0) return RTX_E_BADARG;
+    if (dtype != RTX_F64 && dtype != RTX_F32) return RTX_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    AimDev d;
+    int rc = aim_plan(ctx, spec, n_given, yp, d);
+    if (rc) return rc;
+    if (first + count > ctx->aim_total) return RTX_E_BADARG;
+    if (count == 0) return 0;
+    long long b0, b1;
+    const long long* d_off = nullptr;
+    if (ctx->aim_offsets.empty()) {
+        b0 = first / AIM_BLOCK;
+        b1 = (first + count + AIM_BLOCK - 1) / AIM_BLOCK;
+    } else {
+        const auto& off = ctx->aim_offsets;  // off[b] = rank of block b's first kept ray
+        const long long nb = (long long)off.size() - 1;
+        long long lo = 0, hi = nb;  // last block with off[b] <= first
+        while (lo + 1 < hi) {
+            const long long mid = (lo + hi) / 2;
+            if (off[(size_t)mid] <= first) lo = mid; else hi = mid;
+        }
+        b0 = lo;
+        b1 = b0;
+        while (b1 < nb && off[(size_t)b1] < first + count) ++b1;
+        d_off = ctx->d_aim_offsets;
+    }
+    long long grid = b1 - b0;
+    const long long cap = (long long)ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    if (dtype == RTX_F64)
+        aim_rays_kernel<double><<<(unsigned)grid, 256, 0, ctx->stream>>>(
+            d, (const double*)yp, d_off, b0, b1, first, count, (double*)y0, (double*)u0,
+            (double*)yp_out);
+    else
+        aim_rays_kernel<float><<<(unsigned)grid, 256, 0, ctx->stream>>>(
+            d, (const double*)yp, d_off, b0, b1, first, count, (float*)y0, (float*)u0,
+            (double*)yp_out);
     ctx->launches++;
     return (int)cudaGetLastError();
 }

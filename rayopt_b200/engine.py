@@ -472,6 +472,39 @@ class Engine:
                                       rings, ptr(frame), am, float(z), y0.ptr, u0.ptr))
         return y0, u0
 
+    def aim_rays(self, spec, dtype=np.float64, first=0, count=None, yp=None, want_pupil=False):
+        """rtx_aim_plan + rtx_aim_rays: launch rays `first .. first+count-1` of
+        the bundle a `rtx_aim` record (rays.aim_record) describes, generated in
+        HBM.  `yp`: DEVICE (n,2) FP64 pupil coordinates for GRID_GIVEN.
+        Returns (y0, u0) DeviceArrays, plus the (count,2) pupil coordinates
+        when `want_pupil`."""
+        spec = np.ascontiguousarray(spec)
+        n_given = 0 if yp is None else yp.shape[0]
+        ypp = None if yp is None else yp.ptr
+        total = C.c_int64()
+        check(self.lib.rtx_aim_plan(self.ctx, ptr(spec), n_given, ypp, C.byref(total)))
+        count = total.value - first if count is None else int(count)
+        y0, u0 = self.empty((count, 3), dtype), self.empty((count, 3), dtype)
+        po = self.empty((count, 2), np.float64) if want_pupil else None
+        check(self.lib.rtx_aim_rays(self.ctx, ptr(spec), n_given, ypp, _code(dtype), int(first),
+                                    count, y0.ptr, u0.ptr, None if po is None else po.ptr))
+        return (y0, u0, po) if want_pupil else (y0, u0)
+
+    def aim_rays_into(self, spec, y_dst, u_dst, count, first=0, yp=None):
+        """rtx_aim_rays into existing device rows (DeviceArray views)"""
+        spec = np.ascontiguousarray(spec)
+        check(self.lib.rtx_aim_rays(self.ctx, ptr(spec), 0 if yp is None else yp.shape[0],
+                                    None if yp is None else yp.ptr, _code(y_dst.dtype), int(first),
+                                    int(count), y_dst.ptr, u_dst.ptr, None))
+
+    def aim_count(self, spec, yp=None):
+        """number of rays the record generates (after clipping / filtering)"""
+        spec = np.ascontiguousarray(spec)
+        total = C.c_int64()
+        check(self.lib.rtx_aim_plan(self.ctx, ptr(spec), 0 if yp is None else yp.shape[0],
+                                    None if yp is None else yp.ptr, C.byref(total)))
+        return total.value
+
     def aim_infinite_into(self, y_dst, u_dst, count, rings, frame, pmax, yp=None):
         """rtx_aim_infinite into existing device rows (DeviceArray views)"""
         frame = np.ascontiguousarray(frame, np.float64)

@@ -454,27 +454,53 @@ class ResidentTrace(ResidentMixin):
             a.invalidate()
         self.n[0] = self.system.refractive_index(self.l, 0)
 
+    def rays_device(self, yo, wavelength=None, nrays=11, distribution="hexapolar", filter=False,
+                    stop=None, seed=0):
+        """Launch rays of ``rays_point`` generated in HBM by the general
+        generator (rtx_aim_plan / rtx_aim_rays): the pupil grid (hexapolar,
+        square, triangular, random, meridional / sagittal / cross / tee lines),
+        Pupil.map with its `filter`, Conjugate.aim for finite and infinite
+        objects in every projection, telecentric pupils, curved object
+        surfaces.  ``system.pupil`` (the aiming) stays host Python.  Returns
+        False (nothing done) for the distributions that stay on the host."""
+        from .rays import aim_record, grid_spec
+        s, eng = self.system, self.engine
+        ref, grid = grid_spec(distribution, nrays)
+        if grid is None:
+            return False
+        l = s.wavelengths[0] if wavelength is None else wavelength
+        z, p = s.pupil(yo, l=wavelength, stop=stop)
+        spec = aim_record(s.object, yo, z, p, grid, filter, s[0], seed)
+        count = eng.aim_count(spec)
+        if self._dev is None or self.nrays != count:
+            self.allocate(count)
+        self.l = l
+        self.w = None
+        self._w_default, self._w_dev = True, None
+        self.ref = ref
+        d = self._dev
+        eng.aim_rays_into(spec, d["y"].rows(0), d["u"].rows(0), count)
+        d["i"].rows(0).copy_from(d["u"].rows(0), count*24)   # i[0] = u[0] (geometric_trace.py:68)
+        self._zero_t0()
+        for a in (self.y, self.u, self.i, self.t):
+            a.invalidate()
+        self.n[0] = s.refractive_index(self.l, 0)
+        return True
+
     def rays_point(self, yo, wavelength=None, nrays=11, distribution="hexapolar",
                    filter=None, stop=None, clip=False):
         """GeometricTrace.rays_point (rayopt/geometric_trace.py:204-209) for a
         rayopt ``System``: the pupil is aimed by the reference on the host
-        (``system.pupil``); for an infinite rectilinear object with a plane
-        first surface and the hexapolar distribution the rays are then
-        generated in HBM, otherwise by ``system.aim`` on the host and
-        uploaded.  Traces with `clip`."""
+        (``system.pupil``), the launch rays are generated in HBM
+        (``rays_device``) -- or by ``system.aim`` on the host and uploaded for
+        the quadrature distributions -- and traced with `clip`."""
         s = self.system
-        l = s.wavelengths[0] if wavelength is None else wavelength
-        z, p = s.pupil(yo, l=wavelength, stop=stop)
-        obj = s.object
-        on_device = (distribution == "hexapolar" and not obj.finite and nrays > 1 and
-                     getattr(obj, "projection", "rectilinear") == "rectilinear" and
-                     not getattr(s[0], "curvature", 0.) and
-                     getattr(s[0], "aspherics", None) is None and filter in (None, False) and clip)
-        if on_device:
-            self.rays_infinite(yo, z, p, obj.angle, l=l, nrays=nrays)
-        else:
+        filt = (not clip) if filter is None else filter
+        if not self.rays_device(yo, wavelength, nrays, distribution, filt, stop):
             from rayopt.utils import pupil_distribution      # the reference's own helper
+            l = s.wavelengths[0] if wavelength is None else wavelength
+            z, p = s.pupil(yo, l=wavelength, stop=stop)
             ref, yp, weight = pupil_distribution(distribution, nrays)
-            y, u = s.aim(yo, yp, z, p, filter=(not clip) if filter is None else filter)
+            y, u = s.aim(yo, yp, z, p, filter=filt)
             self.rays_given(y, u, l, weight, ref)
         self.propagate(clip=clip)

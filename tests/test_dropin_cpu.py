@@ -396,14 +396,19 @@ def test_resident_rays_point_matches_reference():
     from rayopt_b200 import ResidentTrace
     from rayopt_b200.rays import hexapolar
 
+    import aim_oracle
+
     class Eng(FakeResidentEngine):
-        def aim_infinite_into(self, y_dst, u_dst, count, rings, frame, pmax, yp=None):
-            assert yp is None
-            xy = hexapolar(count)[1]
-            u, yb, s_, m = (np.asarray(frame[3*k:3*k + 3]) for k in range(4))
-            y = yb + ((xy[:, 0, None]*pmax)*s_ + (xy[:, 1, None]*pmax)*m)
-            y = y + (-y[:, 2]/u[2])[:, None]*u
-            y_dst.a[0, :count], u_dst.a[0, :count] = y, u
+        """the device generator replaced by its numpy restatement"""
+        generated = 0
+
+        def aim_count(self, spec, yp=None):
+            return len(aim_oracle.generate(spec)[0])
+
+        def aim_rays_into(self, spec, y_dst, u_dst, count, first=0, yp=None):
+            y, u, _ = aim_oracle.generate(spec)
+            y_dst.a[0, :count], u_dst.a[0, :count] = y[first:first + count], u[first:first + count]
+            Eng.generated += 1
     s = R.System(**yaml.safe_load(systems_yaml.DOUBLE_GAUSS))
     s.update()
     s.paraxial.refocus()
@@ -415,9 +420,15 @@ def test_resident_rays_point_matches_reference():
     np.testing.assert_allclose(got.y[0], ref.y[0], rtol=0, atol=1e-13)
     np.testing.assert_allclose(np.asarray(got.y), ref.y, rtol=0, atol=1e-11)
     assert np.array_equal(np.isnan(np.asarray(got.u)), np.isnan(ref.u))
-    ref.rays_point((0, 1.), nrays=60, distribution="square", clip=False)
-    got.rays_point((0, 1.), nrays=60, distribution="square", clip=False)
-    assert np.array_equal(np.asarray(got.y), ref.y, equal_nan=True)
+    for dist, n, clip in (("square", 60, False), ("tee", 31, True), ("triangular", 200, True),
+                          ("cross", 21, False), ("radau", 13, False)):
+        ref.rays_point((0, 1.), nrays=n, distribution=dist, clip=clip)
+        got.rays_point((0, 1.), nrays=n, distribution=dist, clip=clip)
+        assert got.ref == ref.ref and got.nrays == ref.y.shape[1], dist
+        assert np.array_equal(np.asarray(got.y), ref.y, equal_nan=True), dist
+        assert np.array_equal(np.asarray(got.u), ref.u, equal_nan=True), dist
+        assert np.array_equal(got.w, ref.w), dist
+    assert Eng.generated == 5                     # radau went through system.aim on the host
 
 
 @pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
