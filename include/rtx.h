@@ -218,6 +218,23 @@ int rtx_trace_batch(rtx_ctx *ctx, int nb, const rtx_surface *const *surf, int S,
                     void *const *I, void *const *T, unsigned flags);
 
 /*
+ * The same with HOST buffers in the reference layout, any number of bundles
+ * (nb >= 1; per bundle y0,u0 (N[b],3) and Y,U,I (rows,N[b],3), T (rows,N[b])):
+ * the front end for callers that issue many SMALL traces of one lens --
+ * Analysis loops 3 fields x 3-5 wavelengths x 150-ray bundles
+ * (rayopt/analysis.py:226-245, 266-280).  All launch rays go up in ONE H2D
+ * from a page-locked bounce buffer, the bundles are marched 8 per launch
+ * (rtx_trace_batch), all results come back in ONE D2H, one synchronisation.
+ * Bundles too large for the bounce buffer are traced one by one through
+ * rtx_trace_host.  Y, U, I, T may each be NULL as a whole.
+ */
+int rtx_trace_batch_host(rtx_ctx *ctx, int nb, const rtx_surface *const *surf,
+                         int S, const double *rot0, int dtype, const int64_t *N,
+                         const void *const *y0, const void *const *u0, int clip,
+                         int keep, void *const *Y, void *const *U,
+                         void *const *I, void *const *T, unsigned flags);
+
+/*
  * Optional warp-ballot vignetting mask for the following rtx_trace /
  * rtx_trace_gather calls on device buffers: dmask (DEVICE, ceil(N/32) words,
  * or NULL to switch it off) receives bit (ray % 32) of word ray / 32 = 1 when

@@ -8,10 +8,10 @@ fallback: importing works anywhere, tracing needs librtx.so and a GPU.
 from .surface_table import (SURFACE_DTYPE, PackedSystem, pack_system,  # noqa: F401
                             pack_element, table_from_json, table_to_json)
 from .geometric_trace import (GeometricTrace, PropagateMixin, bind,  # noqa: F401
-                              system_propagate, install)
+                              system_propagate, install, propagate_many)
 from .engine import Engine, DeviceArray, default_engine  # noqa: F401
 from . import elements  # noqa: F401
-from .lazy import LazyRows, ResidentTrace  # noqa: F401
+from .lazy import LazyRows, ResidentMixin, ResidentTrace  # noqa: F401
 from ._lib import RtxError  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -48,6 +48,8 @@ SYMBOLS = {
                        _vp, _vp, _vp, _vp, _u]),
     "rtx_trace_batch": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i64,
                              _vp, _vp, _vp, _vp, _u]),
+    "rtx_trace_batch_host": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i,
+                                  _vp, _vp, _vp, _vp, _u]),
     "rtx_set_mask_output": (_i, [_vp, _vp]),
     "rtx_set_path_sum_output": (_i, [_vp, _vp, _i]),
     "rtx_trace_host": (_i, [_vp, _vp, _i, _vp, _i, _i64, _vp, _vp, _i, _i,

@@ -1022,6 +1022,143 @@ int rtx_trace_batch(rtx_ctx* ctx, int nb, const rtx_surface* const* surf, int S,
     return 0;
 }
 
+}  // extern "C"
+
+namespace {
+constexpr size_t BATCH_HOST_BYTES = 64u << 20;
+
+template <typename T>
+int trace_batch_host(rtx_ctx* ctx, int nb, const rtx_surface* const* surf, int S,
+                     const double* rot0, const int64_t* N, const void* const* y0,
+                     const void* const* u0, int clip, int keep, void* const* Y, void* const* U,
+                     void* const* I, void* const* Tt, unsigned flags) {
+    const int rows = keep == RTX_KEEP_LAST ? 1 : S;
+    long long nmax = 0, nsum = 0;
+    for (int b = 0; b < nb; ++b) {
+        nmax = N[b] > nmax ? N[b] : nmax;
+        nsum += N[b];
+    }
+    const long long ld = (nmax + 31) / 32 * 32;  // one pitch for all bundles: whole 32-ray groups
+    std::vector<size_t> in_off((size_t)nb);
+    size_t o = 0;
+    for (int b = 0; b < nb; ++b) {  // [y0|u0] of every bundle, 16-byte aligned
+        in_off[(size_t)b] = o;
+        o += ((size_t)N[b] * 6 * sizeof(T) + 15) & ~size_t(15);
+    }
+    (void)nsum;
+    const size_t per3 = (size_t)rows * ld * 3 * sizeof(T), per1 = (size_t)rows * ld * sizeof(T);
+    const size_t per_bundle = (Y ? per3 : 0) + (U ? per3 : 0) + (I ? per3 : 0) + (Tt ? per1 : 0);
+    const size_t in_pad = (o + 255) & ~size_t(255);
+    const size_t need = in_pad + per_bundle * nb;
+    if (need > BATCH_HOST_BYTES) {  // large bundles: one by one through the chunked pipeline
+        for (int b = 0; b < nb; ++b) {
+            if (N[b] == 0) continue;
+            int rc = trace_host<T>(ctx, surf[b], S, rot0, N[b], y0[b], u0[b], clip, keep,
+                                   Y ? Y[b] : nullptr, U ? U[b] : nullptr, I ? I[b] : nullptr,
+                                   Tt ? Tt[b] : nullptr, flags);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    if (need > ctx->small_bytes) {
+        if (ctx->small_host) CK(cudaFreeHost(ctx->small_host));
+        if (ctx->small_dev) CK(cudaFree(ctx->small_dev));
+        ctx->small_host = ctx->small_dev = nullptr;
+        ctx->small_bytes = 0;
+        const size_t cap = need < (256u << 10) ? (256u << 10) : need;
+        CK(cudaMallocHost(&ctx->small_host, cap));
+        CK(cudaMalloc(&ctx->small_dev, cap));
+        ctx->small_bytes = cap;
+    }
+    char* h = (char*)ctx->small_host;
+    char* d = (char*)ctx->small_dev;
+    for (int b = 0; b < nb; ++b) {
+        const size_t v3 = (size_t)N[b] * 3 * sizeof(T);
+        if (!v3) continue;
+        memcpy(h + in_off[(size_t)b], y0[b], v3);
+        memcpy(h + in_off[(size_t)b] + v3, u0[b], v3);
+    }
+    CK(cudaMemcpyAsync(d, h, o, cudaMemcpyHostToDevice, ctx->stream));
+    for (int g0 = 0; g0 < nb; g0 += RTX_MAX_BATCH) {
+        const int g = nb - g0 < RTX_MAX_BATCH ? nb - g0 : RTX_MAX_BATCH;
+        const rtx_surface* gs[RTX_MAX_BATCH];
+        int64_t gn[RTX_MAX_BATCH];
+        const void *gy0[RTX_MAX_BATCH], *gu0[RTX_MAX_BATCH];
+        void *gY[RTX_MAX_BATCH], *gU[RTX_MAX_BATCH], *gI[RTX_MAX_BATCH], *gT[RTX_MAX_BATCH];
+        int m = 0;
+        for (int k = 0; k < g; ++k) {
+            const int b = g0 + k;
+            if (N[b] == 0) continue;
+            char* ob = d + in_pad + per_bundle * b;
+            gs[m] = surf[b];
+            gn[m] = N[b];
+            gy0[m] = d + in_off[(size_t)b];
+            gu0[m] = d + in_off[(size_t)b] + (size_t)N[b] * 3 * sizeof(T);
+            gY[m] = Y ? ob : nullptr;
+            ob += Y ? per3 : 0;
+            gU[m] = U ? ob : nullptr;
+            ob += U ? per3 : 0;
+            gI[m] = I ? ob : nullptr;
+            ob += I ? per3 : 0;
+            gT[m] = Tt ? ob : nullptr;
+            ++m;
+        }
+        if (m == 0) continue;
+        int rc = trace_batch<T>(ctx, m, gs, S, rot0, gn, gy0, gu0, clip, keep, ld, Y ? gY : nullptr,
+                                U ? gU : nullptr, I ? gI : nullptr, Tt ? gT : nullptr, flags);
+        if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(h + in_pad, d + in_pad, per_bundle * nb, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < nb; ++b) {  // (rows, ld, k) on the device -> (rows, N, k) of the caller
+        const char* ob = h + in_pad + per_bundle * b;
+        auto unpack = [&](void* dst, int k) {
+            if (!dst) return;
+            const size_t w = (size_t)N[b] * k * sizeof(T), pitch = (size_t)ld * k * sizeof(T);
+            for (int r = 0; r < rows; ++r) memcpy((char*)dst + r * w, ob + r * pitch, w);
+            ob += (size_t)rows * pitch;
+        };
+        unpack(Y ? Y[b] : nullptr, 3);
+        unpack(U ? U[b] : nullptr, 3);
+        unpack(I ? I[b] : nullptr, 3);
+        unpack(Tt ? Tt[b] : nullptr, 1);
+    }
+    clear_chunk_events(ctx);
+    ctx->kernel_timed = false;
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int rtx_trace_batch_host(rtx_ctx* ctx, int nb, const rtx_surface* const* surf, int S,
+                         const double* rot0, int dtype, const int64_t* N, const void* const* y0,
+                         const void* const* u0, int clip, int keep, void* const* Y,
+                         void* const* U, void* const* I, void* const* T, unsigned flags) {
+    if (!ctx || nb < 1 || !surf || !N || !y0 || !u0) return RTX_E_BADARG;
+    if (keep != RTX_KEEP_ALL && keep != RTX_KEEP_LAST) return RTX_E_BADARG;
+    if (dtype != RTX_F64 && dtype != RTX_F32) return RTX_E_BADARG;
+    for (int b = 0; b < nb; ++b) {
+        int rc = check_table(surf[b], S);
+        if (rc) return rc;
+        if (N[b] < 0 || (N[b] > 0 && (!y0[b] || !u0[b]))) return RTX_E_BADARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    unsigned* saved_mask = ctx->mask;
+    void* saved_tsum = ctx->tsum;
+    ctx->mask = nullptr;
+    ctx->tsum = nullptr;
+    int rc = dtype == RTX_F64
+                 ? trace_batch_host<double>(ctx, nb, surf, S, rot0, N, y0, u0, clip, keep, Y, U, I,
+                                            T, flags)
+                 : trace_batch_host<float>(ctx, nb, surf, S, rot0, N, y0, u0, clip, keep, Y, U, I,
+                                           T, flags);
+    ctx->mask = saved_mask;
+    ctx->tsum = saved_tsum;
+    return rc;
+}
+
 int rtx_trace_host(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot0, int dtype,
                    int64_t N, const void* y0, const void* u0, int clip, int keep, void* Y, void* U,
                    void* I, void* T, unsigned flags) {

@@ -312,6 +312,39 @@ class Engine:
             self._flags(exact, direct, rpt)))
         return tuple(res)
 
+    def trace_bundles(self, tables, y0s, u0s, clip=False, keep_last=False, rot0=None,
+                      dtype=np.float64, exact=False, want=("y", "u", "i", "t")):
+        """rtx_trace_batch_host: many (small) bundles of ONE lens, host arrays
+        in and out, one H2D + launches of 8 bundles + one D2H.  `tables[b]`
+        the table of bundle b (same number of surfaces), `y0s[b]`, `u0s[b]`
+        its (N_b,3) launch rays.  Returns a list of (Y, U, I, T) per bundle
+        (None for arrays not in `want`)."""
+        nb = len(tables)
+        tabs = [self._table(t) for t in tables]
+        S = len(tabs[0])
+        if any(len(t) != S for t in tabs):
+            raise ValueError("all bundles of a batch must have the same number of surfaces")
+        dtype = np.dtype(dtype)
+        y0s = [np.ascontiguousarray(np.atleast_2d(a), dtype) for a in y0s]
+        u0s = [np.ascontiguousarray(np.atleast_2d(a), dtype) for a in u0s]
+        Ns = [a.shape[0] for a in y0s]
+        rows = 1 if keep_last else S
+        outs = {k: ([np.empty((rows, n, 3) if k != "t" else (rows, n), dtype) for n in Ns]
+                    if k in want else None) for k in "yuit"}
+        vp = C.c_void_p
+
+        def arr(items):
+            if items is None:
+                return None
+            return C.cast((vp*nb)(*[vp(a.ctypes.data) for a in items]), vp)
+        keep = [arr(tabs), arr(y0s), arr(u0s)] + [arr(outs[k]) for k in "yuit"]
+        r0 = None if rot0 is None else np.ascontiguousarray(rot0, np.float64).reshape(9)
+        check(self.lib.rtx_trace_batch_host(
+            self.ctx, nb, keep[0], S, ptr(r0), _code(dtype), C.cast((C.c_int64*nb)(*Ns), vp),
+            keep[1], keep[2], int(bool(clip)), RTX_KEEP_LAST if keep_last else RTX_KEEP_ALL,
+            keep[3], keep[4], keep[5], keep[6], self._flags(exact, False)))
+        return [tuple(None if outs[k] is None else outs[k][b] for k in "yuit") for b in range(nb)]
+
     def trace_gather(self, table, y0, u0, dst_ptrs, dst_offset, N=None, clip=False,
                      rot0=None, exact=False, dst_i_ptrs=None):
         """rtx_trace_gather: trace the local shard (DEVICE y0,u0) and store

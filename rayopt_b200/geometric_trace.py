@@ -125,7 +125,11 @@ class PropagateMixin:
 
 
 class GeometricTrace(PropagateMixin):
-    """Standalone drop-in (no rayopt import needed)."""
+    """Standalone drop-in (no rayopt import needed): ``allocate / rays_given /
+    propagate / rms / refocus`` on any `system` the packer can walk.  The ray
+    launch helpers (``rays_point``, ``rays_clipping``, ``rays_line`` ...) are
+    not restated here: with a rayopt ``System`` use ``bind(rayopt.
+    GeometricTrace)``, which inherits the reference's own."""
 
     def __init__(self, system, engine=None, dtype=np.float64, exact=False,
                  alias_incidence=True):
@@ -184,60 +188,40 @@ class GeometricTrace(PropagateMixin):
         self.propagate()
 
 
-    # ---- ray launch helpers of the reference (rayopt/geometric_trace.py:185-229),
-    # for a `system` that offers rayopt's aiming interface (System.pupil / aim /
-    # aim_chief, rayopt/system.py:504-593); ray aiming stays host Python
-    def rays(self, yo, yp, wavelength, stop=None, filter=None, clip=False, weight=None, ref=0):
-        """aim pupil coordinates `yp` from field point `yo`, trace
-        (geometric_trace.py:195-202)"""
-        z, p = self.system.pupil(yo, l=wavelength, stop=stop)
-        y, u = self.system.aim(yo, yp, z, p, filter=(not clip) if filter is None else filter)
-        self.rays_given(y, u, wavelength, weight, ref)
-        self.propagate(clip=clip)
+def propagate_many(traces, clip=False):
+    """``propagate(clip=clip)`` of several traces of ONE lens in one batched
+    call (Engine.trace_bundles -> rtx_trace_batch_host): the front end for
+    Analysis-style loops over fields x wavelengths of small bundles
+    (rayopt/analysis.py:226-245, 266-280) -- launch rays loaded with
+    ``rays_given`` (or by the reference's ``rays`` up to its propagate), then
 
-    def rays_point(self, yo, wavelength=None, nrays=11, distribution="meridional", filter=None,
-                   stop=None, clip=False):
-        """a pupil distribution from one field point (geometric_trace.py:204-209)"""
-        from rayopt.utils import pupil_distribution        # the reference's own grids
-        ref, yp, weight = pupil_distribution(distribution, nrays)
-        self.rays(yo, yp, wavelength, filter=filter, stop=stop, clip=clip, weight=weight, ref=ref)
+        traces = [GT(system) for _ in bundles]
+        for t, (yo, l) in zip(traces, bundles):   # aiming stays host Python
+            z, p = system.pupil(yo, l=l); y, u = system.aim(yo, yp, z, p)
+            t.rays_given(y, u, l, weight, ref)
+        rayopt_b200.propagate_many(traces, clip=True)
 
-    def rays_clipping(self, yo, wavelength=None, axis=1):
-        """chief and the two rim rays along `axis` (geometric_trace.py:211-215)"""
-        z, p = self.system.pupil(yo, l=wavelength, stop=-1)
-        yp = np.zeros((3, 2))
-        yp[1:, axis] = p[:, axis]/np.fabs(p).max()
-        self.rays(yo, yp, wavelength, stop=-1, filter=False)
-
-    def rays_line(self, yo, wavelength=None, nrays=21, eps=1e-2):
-        """chief ray plus a meridional and a sagittal neighbour (pupil offset
-        `eps`) for `nrays` field points from the axis to `yo`
-        (geometric_trace.py:217-229); rows are grouped [chief | meridional |
-        sagittal]"""
-        s = self.system
-        fields = np.linspace(0, 1, nrays)[:, None]*np.atleast_2d(yo)
-        offsets = np.zeros((3, 2))
-        offsets[1, 1] = offsets[2, 0] = eps
-        y = np.empty((3, nrays, 3))
-        u = np.empty((3, nrays, 3))
-        z, p = s.pupil((0, 0), l=wavelength)
-        reach = np.fabs(p).max()
-        for k, f in enumerate(fields):
-            z = s.aim_chief(f, z, reach, l=wavelength)
-            y[:, k], u[:, k] = s.aim(f, offsets, z, p)
-        self.rays_given(y.reshape(-1, 3), u.reshape(-1, 3), wavelength)
-        self.propagate()
-
-    def rays_paraxial(self, paraxial=None):
-        """the two paraxial rays as real rays (geometric_trace.py:185-193)"""
-        par = self.system.paraxial if paraxial is None else paraxial
-        y = np.zeros((2, 2))
-        u = np.zeros((2, 2))
-        y[:, par.axis] = par.y[0]
-        tan_u = np.asarray(par.u[0], float)
-        u[:, par.axis] = tan_u*(1/np.sqrt(1 + np.square(tan_u)))   # sinarctan, utils.py:60-72
-        self.rays_given(y, u)
-        self.propagate()
+    Every trace ends up exactly as after its own ``propagate``."""
+    if not traces:
+        return
+    eng = traces[0]._engine()
+    packs = []
+    for t in traces:
+        t._cache_system()
+        table, n, rot0 = pack_system(t.system, t.l, 1, None, n0=t.n[0])
+        if rot0 is not None:
+            raise ValueError("propagate_many: a rotated object frame needs per-trace propagate")
+        packs.append((table, n))
+        if getattr(t, "_i_alias", False) and (table["flags"] & 1).any():
+            t._materialize_i()
+    res = eng.trace_bundles([p[0] for p in packs], [t.y[0] for t in traces],
+                            [t.u[0] for t in traces], clip=clip, exact=traces[0].exact)
+    for t, (table, n), (Y, U, I, T) in zip(traces, packs, res):
+        rows = len(table)
+        t.y[1:1 + rows], t.u[1:1 + rows], t.t[1:1 + rows] = Y, U, T
+        if not getattr(t, "_i_alias", False):
+            t.i[1:1 + rows] = I
+        t.n[1:1 + rows] = n
 
 
 def bind(reference_trace_class, engine=None, dtype=np.float64, exact=False, resident=False,

@@ -33,6 +33,11 @@ class OracleEngine:
     def pinned_empty(self, shape, dtype):
         return np.empty(shape, dtype)
 
+    def trace_bundles(self, tables, y0s, u0s, clip=False, keep_last=False, rot0=None,
+                      dtype=np.float64, exact=False, want=("y", "u", "i", "t")):
+        OracleEngine.calls += 1
+        return [np_oracle.trace(t, y, u, clip=clip) for t, y, u in zip(tables, y0s, u0s)]
+
 
 def _packed(name):
     ent = load_systems()[name]
@@ -432,26 +437,33 @@ def test_resident_rays_point_matches_reference():
 
 
 @pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
-def test_standalone_ray_launch_helpers_match_reference():
-    """GeometricTrace.rays / rays_point / rays_clipping / rays_paraxial of the
-    standalone class (geometric_trace.py:185-215 restated) on a reference
-    System give the reference's traces"""
+def test_propagate_many_equals_individual_propagates():
+    """propagate_many: the Analysis pattern (fields x wavelengths of small
+    bundles, analysis.py:266-280) in one batched call leaves every bound trace
+    exactly as its own propagate would"""
+    import rayopt_b200
     warnings.simplefilter("ignore")
     R = ref_shim.load()
     s = R.System(**yaml.safe_load(systems_yaml.COOKE))
     s.update()
     s.paraxial.refocus()
-    s.paraxial.update_conjugates()
-    ref, got = R.GeometricTrace(s), GeometricTrace(s, engine=OracleEngine())
-    for fn, args, kw in (("rays_point", ((0, 1.),), dict(nrays=40, distribution="hexapolar", clip=True)),
-                         ("rays_point", ((0, .5),), dict(nrays=9, distribution="meridional")),
-                         ("rays_clipping", ((0, 1.),), {}),
-                         ("rays_line", ((0, 1.),), dict(nrays=5)),
-                         ("rays_paraxial", (), {}),
-                         ("rays", ((0, .7), np.array([[0, 0], [.5, .5], [-.3, .9]]), s.wavelengths[1]),
-                          dict(clip=True))):
-        getattr(ref, fn)(*args, **kw)
-        getattr(got, fn)(*args, **kw)
+    GT = bind(R.GeometricTrace, engine=OracleEngine())
+    ref_, yp, weight = R.utils.pupil_distribution("hexapolar", 150)
+    refs, traces = [], []
+    for hi in (1., .707, 0.):
+        for wi in s.wavelengths:
+            r = R.GeometricTrace(s)
+            r.rays_point((0, hi), wi, nrays=150, distribution="hexapolar", clip=True)
+            refs.append(r)
+            t = GT(s)
+            z, p = s.pupil((0, hi), l=wi)
+            y, u = s.aim((0, hi), yp, z, p, filter=False)
+            t.rays_given(y, u, wi, weight, ref_)
+            traces.append(t)
+    calls0 = OracleEngine.calls
+    rayopt_b200.propagate_many(traces, clip=True)
+    assert OracleEngine.calls == calls0 + 1
+    for r, t in zip(refs, traces):
         for k in "yuit":
-            assert np.array_equal(getattr(got, k), getattr(ref, k), equal_nan=True), (fn, k)
-        assert np.array_equal(got.n, ref.n) and got.ref == ref.ref
+            assert np.array_equal(getattr(t, k), getattr(r, k), equal_nan=True), k
+        assert np.array_equal(t.n, r.n) and np.array_equal(t.path, r.path)

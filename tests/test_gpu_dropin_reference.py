@@ -281,3 +281,43 @@ def test_bound_trace_other_lenses(R, eng, lens, n):
     res.rays((0, .7), yp, s.wavelengths[0], clip=lens != "mirror", filter=False)
     same(res, ref, False, lens + " resident")
     res.free()
+
+
+def test_batched_host_front_end(R, eng):
+    """rtx_trace_batch_host / propagate_many: Analysis' 3 fields x 3 wavelengths
+    of 150-ray hexapolar bundles (analysis.py:266-280), plus ragged sizes and
+    more than 8 bundles, in ONE call -- bit-identical (RTX_EXACT) to the
+    reference's own rays_point loops"""
+    import rayopt_b200
+    s = build(R, "cooke")
+    GT = rayopt_b200.bind(R.GeometricTrace, engine=eng, exact=True)
+    refs, traces = [], []
+    for k, hi in enumerate((1., .707, 0., .3)):
+        for wi in s.wavelengths:
+            n = 150 + 37*k
+            ref_, yp, weight = R.utils.pupil_distribution("hexapolar", n)
+            r = R.GeometricTrace(s)
+            r.rays_point((0, hi), wi, nrays=n, distribution="hexapolar", clip=True)
+            refs.append(r)
+            t = GT(s)
+            z, p = s.pupil((0, hi), l=wi)
+            t.rays_given(*s.aim((0, hi), yp, z, p, filter=False), wi, weight, ref_)
+            traces.append(t)
+    assert len(traces) == 12
+    l0 = eng.launch_count()
+    rayopt_b200.propagate_many(traces, clip=True)
+    assert eng.launch_count() - l0 == 2              # 8 + 4 bundles: two launches
+    for r, t in zip(refs, traces):
+        same(t, r, True, "batched")
+    # the raw call: ragged bundles incl. a single ray and an empty one, keep-LAST
+    from rayopt_b200.surface_table import pack_system
+    table, _, _ = pack_system(s, s.wavelengths[0])
+    ys = [refs[0].y[0], refs[3].y[0][:1], refs[6].y[0][:0], refs[9].y[0]]
+    us = [refs[0].u[0], refs[3].u[0][:1], refs[6].u[0][:0], refs[9].u[0]]
+    out = eng.trace_bundles([table]*4, ys, us, clip=True, keep_last=True, exact=True,
+                            want=("y", "t"))
+    for (Y, U, I, T), y0, u0 in zip(out, ys, us):
+        want = eng.trace(table, y0, u0, clip=True, keep_last=True, exact=True) if len(y0) else None
+        assert U is None and I is None and Y.shape == (1, len(y0), 3)
+        if want is not None:
+            assert np.array_equal(Y, want[0], equal_nan=True) and np.array_equal(T, want[3], equal_nan=True)
