@@ -341,16 +341,19 @@ def leg_c5(eng, dist, torch, exact, NR=10_000_000):
         lo, hi = max(g0, b*N) - b*N, min(g1, (b + 1)*N) - b*N
         if hi > lo:
             segs.append((b, lo, hi))
+    # one result set, sized for the longest segment and reused by every segment
+    # of the rank (a throughput measurement: each launch stores its full trace;
+    # 25 resident result sets would be 412 GB)
+    ldmax = (max(hi - lo for _, lo, hi in segs) + 127)//128*128
+    out = [eng.empty((S, ldmax, 3)) for _ in range(3)] + [eng.empty((S, ldmax))]
     work = []
     for b, lo, hi in segs:
         fi, li = bundles[b]
         aim = ent["aim"][li][fi]
         y0, u0 = eng.aim_infinite_device(aim["field"], aim["z"], aim["p"], ent["object_angle"],
                                          nrays=NR)
-        n = hi - lo
-        ld = (n + 63)//64*64
-        out = [eng.empty((S, ld, 3)) for _ in range(3)] + [eng.empty((S, ld))]
-        work.append((ent["tables"][li], y0.rows(lo, hi), u0.rows(lo, hi), out, n, ld, y0, u0))
+        work.append((ent["tables"][li], y0.rows(lo, hi), u0.rows(lo, hi), out, hi - lo, ldmax,
+                     y0, u0))
 
     def step():
         for table, y0, u0, out, n, ld, _, _ in work:
@@ -376,8 +379,10 @@ def leg_c5(eng, dist, torch, exact, NR=10_000_000):
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     mine = sum(w[4] for w in work)
     for w in work:
-        for a in w[3] + [w[6], w[7]]:
-            a.free()
+        w[6].free()
+        w[7].free()
+    for a in out:
+        a.free()
     return {"workload": "C5: zoom S=20, 5 fields x 5 wavelengths x %d rays (25 bundles, split by "
                         "rays: %.3f bundles per rank), FP64, full trace stored" % (N, 25/world),
             "rays_this_rank": mine, "segments_this_rank": len(work),
