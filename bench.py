@@ -301,9 +301,30 @@ def leg_c4(eng, dist, torch, exact, n_local=125_000_000):
     m_full = eng.moments(pg.buf, N=n_local*world, center=center[:2])
     mom_err = float(np.max(np.abs(m[:8] - m_full)/np.maximum(np.abs(m_full), 1e-300)))
     mom_ok = bool(m[5] == n_local*world and m[4] == m_full[4] and mom_err < 1e-11)
-    ok = torch.tensor([1.0 if (par["ok"] and mom_ok) else 0.0], device="cuda")
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     pg.close()
+    # the same gather of (x, y) only (RTX_GATHER_XY): what a spot diagram reads,
+    # 16 instead of 24 bytes per ray over NVLink
+    pg2 = PeerGather(eng, dist, n_local*world, xy=True)
+
+    def run_xy():
+        eng.trace_gather(table, y0, u0, pg2.ptrs, pg2.b[rank], N=n_local, clip=True, exact=exact,
+                         xy=True)
+        eng.sync()
+        dist.barrier()
+    run_xy()
+    kxy = []
+    for _ in range(3):
+        run_xy()
+        kxy.append(eng.last_kernel_ms())
+    kxy_max = maxr_t(torch, dist, statistics.median(kxy))
+    got_xy = np.empty((len(idx), 2))
+    for j, i in enumerate(pg2.b[peer] + idx):
+        eng.lib.rtx_memcpy_d2h(eng.ctx, got_xy[j].ctypes.data, pg2.buf.ptr + int(i)*16, 16)
+    eng.sync()
+    par_xy = check_sample(got_xy, want[:, :2], "peer segment (x,y)")
+    pg2.close()
+    ok = torch.tensor([1.0 if (par["ok"] and mom_ok and par_xy["ok"]) else 0.0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     y0.free()
     u0.free()
     stats = {"api": "rtx_trace_reduce per rank + ONE NCCL all-reduce of 20 doubles",
@@ -311,6 +332,10 @@ def leg_c4(eng, dist, torch, exact, n_local=125_000_000):
              "rays_total": n_local*world, "rays_arrived": float(m[4]),
              "vs_rtx_moments_of_gathered_spot_rel_err": mom_err, "ok": mom_ok}
     return {"statistics_path": stats,
+            "xy_only": {"kernel_ms_max_over_ranks": kxy_max,
+                        "nvlink_bytes_sent_per_rank": (world - 1)*n_local*16,
+                        "nvlink_GBps_per_rank": (world - 1)*n_local*16/(kxy_max*1e-3)/1e9,
+                        "parity_this_rank": par_xy},
             "workload": "C4: Double-Gauss, %d rays per rank (%.3g total) generated in HBM, FP64, "
                         "trace + gather of y[-1] to all %d ranks in one kernel per rank"
                         % (n_local, n_local*world, world),

@@ -71,6 +71,10 @@ extern "C" {
                                of the shared-memory staged bulk (TMA) stores */
 #define RTX_RPT1       4u /* tuning: one ray per thread  (default: library's choice) */
 #define RTX_RPT2       8u /* tuning: two rays per thread */
+#define RTX_GATHER_XY 16u /* rtx_trace_gather: the intercept buffers dst[k] are
+                             (Ntotal, 2) arrays receiving x,y only -- what a spot
+                             diagram reads (rayopt/analysis.py:274): 16 instead of
+                             24 bytes per ray over NVLink */
 
 /* errors */
 #define RTX_OK              0

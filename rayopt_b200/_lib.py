@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "librtx.so")
 
 RTX_F64, RTX_F32 = 0, 1
 RTX_KEEP_ALL, RTX_KEEP_LAST = 0, 1
-RTX_EXACT, RTX_STORE_DIRECT, RTX_RPT1, RTX_RPT2 = 1, 2, 4, 8
+RTX_EXACT, RTX_STORE_DIRECT, RTX_RPT1, RTX_RPT2, RTX_GATHER_XY = 1, 2, 4, 8, 16
 
 # every symbol include/rtx.h declares: name -> (restype, argtypes)
 _vp, _i, _i64, _sz, _u = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_uint

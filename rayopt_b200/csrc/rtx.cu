@@ -308,6 +308,7 @@ struct PeerDst {
     void* ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void* ptr_i[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool has_i = false;
+    bool xy = false;
 };
 
 template <typename T>
@@ -343,12 +344,14 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
         p.npeer = peers->n;
         p.peer_off = peers->off;
         p.peer_has_i = peers->has_i ? 1 : 0;
+        p.peer_xy = peers->xy ? 1 : 0;
         for (int k = 0; k < peers->n; ++k) {
             p.peer[k] = (T*)peers->ptr[k];
             p.peer_i[k] = (T*)peers->ptr_i[k];
         }
         // bulk stores need 16-byte aligned runs in every destination
-        peers_ok = (peers->off * 3 * (long long)sizeof(T)) % 16 == 0;
+        peers_ok = (peers->off * (peers->xy ? 2 : 3) * (long long)sizeof(T)) % 16 == 0 &&
+                   (!peers->has_i || (peers->off * 3 * (long long)sizeof(T)) % 16 == 0);
         for (int k = 0; k < peers->n; ++k) {
             peers_ok = peers_ok && (reinterpret_cast<uintptr_t>(peers->ptr[k]) & 15u) == 0;
             peers_ok = peers_ok && (reinterpret_cast<uintptr_t>(peers->ptr_i[k]) & 15u) == 0;
@@ -1234,6 +1237,7 @@ int rtx_trace_gather(rtx_ctx* ctx, const rtx_surface* surf, int S, const double*
     pd.n = npeers;
     pd.off = dst_offset;
     pd.has_i = dst_i != nullptr;
+    pd.xy = (flags & RTX_GATHER_XY) != 0;
     for (int k = 0; k < npeers; ++k) {
         if (!dst[k] || (dst_i && !dst_i[k])) return RTX_E_BADARG;
         pd.ptr[k] = dst[k];

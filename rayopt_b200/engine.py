@@ -346,11 +346,12 @@ class Engine:
         return [tuple(None if outs[k] is None else outs[k][b] for k in "yuit") for b in range(nb)]
 
     def trace_gather(self, table, y0, u0, dst_ptrs, dst_offset, N=None, clip=False,
-                     rot0=None, exact=False, dst_i_ptrs=None):
+                     rot0=None, exact=False, dst_i_ptrs=None, xy=False):
         """rtx_trace_gather: trace the local shard (DEVICE y0,u0) and store
         the last surface's intercepts into every buffer of `dst_ptrs` (raw
         device pointers: local or peer memory) at ray offset `dst_offset`;
-        `dst_i_ptrs`: a second set of buffers for the incidence directions."""
+        `dst_i_ptrs`: a second set of buffers for the incidence directions;
+        `xy`: the intercept buffers are (Ntotal, 2) and receive x,y only."""
         table = self._table(table)
         N = y0.shape[0] if N is None else int(N)
         r0 = None if rot0 is None else np.ascontiguousarray(rot0, np.float64).reshape(9)
@@ -364,7 +365,7 @@ class Engine:
         check(self.lib.rtx_trace_gather(
             self.ctx, ptr(table), len(table), ptr(r0), _code(y0.dtype), N, y0.ptr, u0.ptr,
             int(bool(clip)), len(dst_ptrs), C.cast(arr, C.c_void_p), arr_i, int(dst_offset),
-            self._flags(exact, False)))
+            self._flags(exact, False) | (_lib.RTX_GATHER_XY if xy else 0)))
 
     # ---- fused epilogues (no per-surface stores) -------------------------
     def trace_reduce(self, table, y0, u0, N=None, clip=False, rot0=None, exact=False, w=None,

@@ -178,14 +178,16 @@ class PeerGather:
 
     ALIGN = 64
 
-    def __init__(self, engine, dist, n_total, dtype=np.float64):
-        self.eng, self.dist = engine, dist
+    def __init__(self, engine, dist, n_total, dtype=np.float64, xy=False):
+        """`xy`: gather x,y only -- (n_total, 2) buffers, 16 instead of 24 bytes
+        per ray over NVLink (what a spot diagram reads)"""
+        self.eng, self.dist, self.xy = engine, dist, bool(xy)
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         if self.world > 8:
             raise ValueError("at most 8 peers (one NVSwitch box)")
         self.n = int(n_total)
         self.npad = (self.n + self.ALIGN - 1)//self.ALIGN*self.ALIGN + self.ALIGN
-        self.buf = engine.empty((self.npad, 3), dtype)
+        self.buf = engine.empty((self.npad, 2 if xy else 3), dtype)
         handles = [None]*self.world
         dist.all_gather_object(handles, engine.ipc_export(self.buf))
         self._opened = []
@@ -208,7 +210,8 @@ class PeerGather:
         n_local = self.b[self.rank + 1] - self.b[self.rank]
         if n_local:
             self.eng.trace_gather(table, y0_local_dev, u0_local_dev, self.ptrs,
-                                  self.b[self.rank], N=n_local, clip=clip, exact=exact)
+                                  self.b[self.rank], N=n_local, clip=clip, exact=exact,
+                                  xy=self.xy)
         self.eng.sync()
         self.dist.barrier()          # every rank's stores have landed everywhere
         return self.buf.download()[:self.n]

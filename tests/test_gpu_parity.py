@@ -393,6 +393,17 @@ def test_trace_gather_epilogue(eng, systems, n, off, with_i):
             assert np.isnan(h[:off]).all()            # nothing written in front of the shard
             assert np.isnan(h[off + n:]).all()        # ... nor behind it
             b.free()
+    # (x,y)-only gather (RTX_GATHER_XY): (N,2) buffers, same rays, same guarantees
+    bxy = [eng.empty((npad, 2)) for _ in range(2)]
+    for b in bxy:
+        eng.lib.rtx_memset(eng.ctx, b.ptr, 0xff, b.nbytes)
+    eng.trace_gather(table, d_y0, d_u0, [b.ptr for b in bxy], off, clip=True, xy=True)
+    eng.sync()
+    for b in bxy:
+        h = b.download()
+        assert np.array_equal(h[off:off + n], ref_y[0][:, :2], equal_nan=True)
+        assert np.isnan(h[:off]).all() and np.isnan(h[off + n:]).all()
+        b.free()
     d_y0.free()
     d_u0.free()
 
