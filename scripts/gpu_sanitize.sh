@@ -15,15 +15,15 @@ ref = eng.trace(table, y0, u0, clip=True, direct=True)
 for kw in (dict(), dict(rpt=1), dict(rpt=2), dict(exact=True), dict(dtype=np.float32), dict(keep_last=True)):
     out = eng.trace(table, y0, u0, clip=True, **kw)
     print(kw, out[0].shape, flush=True)
-ya, ua = y0[:40064], u0[:40064]                         # FP32 four-rays-per-thread kernels (ld % 128 == 0)
+ya, ua = y0[:39936], u0[:39936]                         # FP32 four-rays-per-thread kernels (ld % 128 == 0)
 d32 = [eng.to_device(ya, np.float32), eng.to_device(ua, np.float32)]
-o32 = [eng.empty((len(table), 40064, 3), np.float32) for _ in range(3)] + [eng.empty((len(table), 40064), np.float32)]
-eng.trace_device(table, d32[0], d32[1], *o32, N=40064, ld=40064, clip=True)
+o32 = [eng.empty((len(table), 39936, 3), np.float32) for _ in range(3)] + [eng.empty((len(table), 39936), np.float32)]
+eng.trace_device(table, d32[0], d32[1], *o32, N=39936, ld=39936, clip=True)
 ca = load_systems()["cooke_asph"]["tables"][0]          # Newton kernels: FP64 2x8 per-CTA, FP32 4x8 per-warp
 for dt in (np.float64, np.float32):
     dd = [eng.to_device(ya, dt), eng.to_device(ua, dt)]
-    oo = [eng.empty((len(ca), 40064, 3), dt) for _ in range(3)] + [eng.empty((len(ca), 40064), dt)]
-    eng.trace_device(ca, dd[0], dd[1], *oo, N=40064, ld=40064, clip=True)
+    oo = [eng.empty((len(ca), 39936, 3), dt) for _ in range(3)] + [eng.empty((len(ca), 39936), dt)]
+    eng.trace_device(ca, dd[0], dd[1], *oo, N=39936, ld=39936, clip=True)
 eng.sync()
 print("fp32 rpt4 / newton configs ok", flush=True)
 # side outputs, fused gather destinations, batched bundles

@@ -114,7 +114,7 @@ def test_finite_conjugate(eng, z, telecentric):
         y, u, p = device(eng, rec)
         assert np.array_equal(y, wy) and np.array_equal(p, wp)
         np.testing.assert_allclose(u, wu, rtol=0, atol=4e-16)        # tan(): last ulps
-        np.testing.assert_allclose(np.square(u).sum(1), 1, rtol=0, atol=3e-16)
+        np.testing.assert_allclose(np.square(u).sum(1), 1, rtol=0, atol=7e-16)
 
 
 def test_given_coordinates_and_random(eng):
