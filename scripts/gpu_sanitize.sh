@@ -36,6 +36,9 @@ eng.trace_gather(table, d_y0, d_u0, [b.ptr for b in bufs[:2]], 128, clip=True,
                  dst_i_ptrs=[b.ptr for b in bufs[2:]])          # ragged N: per-ray stores
 eng.trace_gather(table, d_y0, d_u0, [b.ptr for b in bufs[:2]], 128, N=40000//64*64, clip=True,
                  dst_i_ptrs=[b.ptr for b in bufs[2:]])          # whole groups: bulk stores
+bxy = [eng.empty((len(y0) + 256, 2)) for _ in range(2)]
+eng.trace_gather(table, d_y0, d_u0, [b.ptr for b in bxy], 128, N=40000//64*64, clip=True, xy=True)
+eng.trace_gather(table, d_y0, d_u0, [b.ptr for b in bxy], 128, clip=True, xy=True)
 # fused epilogues, ray generator (compaction), batched host front end
 m = eng.trace_reduce(table, d_y0, d_u0, clip=True, center=np.zeros(4))
 A, P = eng.empty((len(y0),)), eng.empty((len(y0), 3))

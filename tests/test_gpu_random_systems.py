@@ -133,8 +133,7 @@ def eng():
 @pytest.mark.parametrize("seed", range(24))
 def test_random_analytic_unrotated_bit_exact(eng, seed):
     """planes / spheres / conics, mirrors, apertures: RTX_EXACT is bit-identical
-    to the oracle; the fast mode is within 1e-10 wherever the reference's own
-    formula is well conditioned"""
+    to the oracle; the fast mode is within 1e-10 on every ray"""
     rng = np.random.default_rng(1000 + seed)
     S = int(rng.integers(2, 24))
     table = random_table(rng, S, rotated=False, newton=False)
@@ -145,19 +144,21 @@ def test_random_analytic_unrotated_bit_exact(eng, seed):
     got = eng.trace(table, y0, u0, clip=clip, exact=True)
     for a, b, w in zip(got, want, "yuit"):
         assert np.array_equal(a, b, equal_nan=True), "seed %d %s" % (seed, w)
-    # (no reference_accurate() filter here: the fast mode evaluates the
-    # cancellation-prone analytic intercept with the reference's own roundings)
-    ok = well_conditioned(table, y0, u0, want, clip)
-    assert ok.mean() > .5, ok.mean()
+    # the default fast mode on ALL rays, no conditioning filter: it evaluates the
+    # cancellation-prone analytic intercept with the reference's own roundings,
+    # so even grazing / near-TIR / aperture-edge rays stay within 1e-10 with an
+    # identical NaN mask (measured worst 1.6e-12 over these seeds,
+    # profiles/r2e_fast_mode_conditioning.txt)
     got = eng.trace(table, y0, u0, clip=clip)
-    for a, b, w in zip(masked(got, ok), masked(want, ok), "yuit"):
+    for a, b, w in zip(got, want, "yuit"):
         assert_parity(a, b, 1e-10, "seed %d fast %s" % (seed, w))
 
 
 @pytest.mark.parametrize("seed", range(16))
 def test_random_general_systems(eng, seed):
-    """+ tilts / decentres and even aspheres (Newton): a few ulp in exact
-    mode (BLAS-ordered dot products in the reference), 1e-10 in fast mode"""
+    """+ tilts / decentres and even aspheres (Newton): 1e-10 on every ray in
+    both modes; a few ulp (1e-11) in exact mode on the well-conditioned rays
+    (BLAS-ordered dot products in the reference)"""
     rng = np.random.default_rng(2000 + seed)
     S = int(rng.integers(2, 16))
     table = random_table(rng, S, rotated=True, newton=True)
@@ -166,13 +167,20 @@ def test_random_general_systems(eng, seed):
     y0, u0 = random_rays(rng, n)
     clip = bool(seed % 2)
     want = np_oracle.trace(table, y0, u0, clip=clip, rot0=rot0)
+    # fast mode: ALL rays, no filter (worst 6.5e-14 over these seeds)
+    got = eng.trace(table, y0, u0, clip=clip, rot0=rot0)
+    for a, b, w in zip(got, want, "yuit"):
+        assert_parity(a, b, 1e-10, "seed %d fast %s" % (seed, w))
+    # exact mode at 1e-11 where the reference's BLAS-ordered dot products (rotations,
+    # Newton fprime) are not amplified by the ray's own conditioning
     ok = (well_conditioned(table, y0, u0, want, clip, rot0) &
           reference_accurate(table, y0, u0, want, clip, rot0))
     assert ok.mean() > .4, ok.mean()
-    for exact, rtol in ((True, 1e-11), (False, 1e-10)):
-        got = eng.trace(table, y0, u0, clip=clip, rot0=rot0, exact=exact)
-        for a, b, w in zip(masked(got, ok), masked(want, ok), "yuit"):
-            assert_parity(a, b, rtol, "seed %d exact=%s %s" % (seed, exact, w))
+    got = eng.trace(table, y0, u0, clip=clip, rot0=rot0, exact=True)
+    for a, b, w in zip(masked(got, ok), masked(want, ok), "yuit"):
+        assert_parity(a, b, 1e-11, "seed %d exact %s" % (seed, w))
+    for a, b, w in zip(got, want, "yuit"):       # ... and 1e-10 on all rays
+        assert_parity(a, b, 1e-10, "seed %d exact all %s" % (seed, w))
     # FP32 on random wild systems: the error is (condition number) x (FP32
     # rounding accumulated over ~100 operations per surface); rays with an
     # amplification below 30 stay within 1e-4 of the lens size -- that is the
