@@ -514,6 +514,7 @@ void clear_chunk_events(rtx_ctx* ctx) {
 }
 
 constexpr size_t SMALL_PATH_BYTES = 4u << 20;
+constexpr size_t ZERO_COPY_BYTES = 16u << 10;  // rays + results of a zero-copy small trace
 
 // Latency path for small bundles (aim_chief / aim_marginal issue hundreds of
 // 1-3 ray traces, rayopt/system.py:507-555): one pinned bounce buffer, ONE
@@ -537,18 +538,25 @@ int trace_host_small(rtx_ctx* ctx, const rtx_surface* surf, int S, const double*
         ctx->small_bytes = nb;
     }
     char* h = (char*)ctx->small_host;
-    char* d = (char*)ctx->small_dev;
     const size_t v3 = (size_t)N * 3 * sizeof(T), r3 = (size_t)rows * v3, r1 = r3 / 3;
     memcpy(h, y0, v3);
     memcpy(h + v3, u0, v3);
-    CK(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // A handful of rays (ray aiming: 1-3): ZERO-COPY.  Page-locked memory is
+    // mapped into the device's address space (UVA), so the kernel reads the
+    // launch rays and writes its results straight over PCIe -- launch + one
+    // synchronisation, no copy-engine round trips (2 x ~8 us).  Beyond
+    // ZERO_COPY_BYTES the DMA engines win: one H2D, the kernel, one D2H.
+    const bool zero_copy = need <= ZERO_COPY_BYTES && !getenv("RTX_NO_ZERO_COPY");
+    char* d = zero_copy ? h : (char*)ctx->small_dev;
+    if (!zero_copy) CK(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     char* dY = d + in_bytes;
     char *dU = dY + r3, *dI = dU + r3, *dT = dI + r3;
     int rc = trace_device<T>(ctx, surf, S, rot0, N, d, d + v3, clip, keep, N, Y ? dY : nullptr,
                              U ? dU : nullptr, I ? dI : nullptr, Tt ? dT : nullptr,
                              flags | RTX_STORE_DIRECT, ctx->stream, nullptr);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h + in_bytes, dY, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!zero_copy)
+        CK(cudaMemcpyAsync(h + in_bytes, dY, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const char* o = h + in_bytes;
     if (Y) memcpy(Y, o, r3);

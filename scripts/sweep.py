@@ -20,6 +20,8 @@ ap.add_argument("--system", default="double_gauss")
 ap.add_argument("--dtype", default="f64")
 ap.add_argument("--device-rays", type=int, default=0,
                 help="1: hexapolar launch rays generated in HBM (large bundles)")
+ap.add_argument("--pad", type=int, default=0, help="extra rays of row pitch (ld = N rounded + pad)")
+ap.add_argument("--gap", type=int, default=0, help="bytes of dummy allocation between the result arrays")
 ap.add_argument("cfgs", nargs="*", default=["2,2,16,1,0,0,1"])
 a = ap.parse_args()
 ent = bench.load_system(a.system)
@@ -35,9 +37,15 @@ if a.device_rays:
 else:
     y0, u0 = bench.make_rays(ent, 0, N, 0)
     d_y0, d_u0 = mem.to_device(y0, dt), mem.to_device(u0, dt)
-ld = ((N + 127)//128)*128
-Y, U, I = (mem.empty((S, ld, 3), dt) for _ in range(3))
-T = mem.empty((S, ld), dt)
+ld = ((N + 127)//128)*128 + a.pad
+gaps = []
+def _arr(shape):
+    if a.gap:
+        gaps.append(mem.empty((a.gap,), np.uint8))
+    return mem.empty(shape, dt)
+Y, U, I = (_arr((S, ld, 3)) for _ in range(3))
+T = _arr((S, ld))
+print("ld %d pad %d gap %d  bases %s" % (ld, a.pad, a.gap, [hex(x.ptr) for x in (Y, U, I, T)]), flush=True)
 alg = N*(6*w + 10*w*S)
 for cfg in a.cfgs:
     if cfg == "default":          # the library's own heuristics (no RTX_* knob set)
