@@ -25,6 +25,7 @@ y,u,i,t stored).  Metric: ray-surface intersections per second.
             numpy port as fallback
   headline  (N=1, when the HBM is free) the north-star point: zoom S=20,
             1e8 rays, FP64, full trace resident, one launch
+  c3        (N=1) BASELINE config C3: Cooke + aspheres, 1e8 rays, FP32
   multi_gpu (N>1) C4: every rank traces 1.25e8 rays generated in HBM and the
             SAME kernel stores y[-1] into the gather buffers of all ranks over
             NVLink (rtx_trace_gather); C5: the 25 zoom bundles split by rays
@@ -242,6 +243,50 @@ def maxr_t(torch, dist, x):
     t = torch.tensor([float(x)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def leg_c3(eng):
+    """BASELINE config C3 on one GPU: Cooke triplet with even aspheres (Newton
+    intercept on 3 of 8 surfaces), ~1e8 rays generated in HBM, FP32, full
+    trace resident (34 GB), one launch"""
+    from rayopt_b200.rays import aim_infinite, hexapolar_xy
+    import np_oracle
+    ent = load_system("cooke_asph")
+    S, table, aim = ent["S"], ent["tables"][0], ent["aim"][0][FIELD_INDEX]
+    rings = int(np.sqrt(1e8/3. - 1/12.) - 1/2.)
+    y0, u0 = eng.aim_infinite_device(aim["field"], aim["z"], aim["p"], ent["object_angle"],
+                                     rings=rings, dtype=np.float32)
+    N = y0.shape[0]//128*128
+    need = S*N*40
+    if eng.free_bytes() < need + (2 << 30):
+        y0.free(), u0.free()
+        return {"skipped": "needs %.1f GB of HBM" % (need/1e9)}
+    out = [eng.empty((S, N, 3), np.float32) for _ in range(3)] + [eng.empty((S, N), np.float32)]
+    ms = []
+    for _ in range(4):
+        eng.trace_device(table, y0, u0, *out, N=N, ld=N, clip=True)
+        ms.append(eng.last_kernel_ms())
+    k_ms = statistics.median(ms[1:])
+    idx = np.unique(np.r_[0, np.random.default_rng(6).integers(1, N, 1500)])
+    hy, hu = aim_infinite(aim["field"], hexapolar_xy(idx, rings), aim["z"], aim["p"],
+                          ent["object_angle"])
+    want = np_oracle.trace(table, hy, hu, clip=True)[0]
+    got = np.stack([eng.download_rays(out[0].rows(j), idx) for j in range(S)]).astype(np.float64)
+    flips = np.isnan(got) != np.isnan(want)         # rays within FP32 of an aperture edge
+    both = ~np.isnan(got) & ~np.isnan(want)
+    err = float(np.max(np.abs(got - want)[both]/np.maximum(np.abs(want[both]), 1.0)))
+    par = {"what": "C3 FP32 y sample of %d rays vs the FP64 oracle" % len(idx),
+           "max_rel_err": err, "nan_mask_flips": int(flips.sum()), "entries": int(flips.size),
+           "ok": bool(err <= 1e-5 and flips.mean() < 5e-3)}
+    for a in [y0, u0] + out:
+        a.free()
+    alg = N*(24 + 40*S)
+    peak, _ = peaks()
+    return {"workload": "C3: Cooke + even aspheres S=8, %d rays generated in HBM, FP32, clip, full "
+                        "trace resident, one launch" % N,
+            "kernel_ms": k_ms, "all_ms": ms, "ray_surfaces_per_s": N*S/k_ms*1e3,
+            "achieved_GBps": alg/k_ms/1e6, "frac": alg/k_ms/1e6/peak, "algorithmic_bytes": alg,
+            "dtype": "f32", "parity": par}
 
 
 def leg_c4(eng, dist, torch, exact, n_local=125_000_000):
@@ -639,11 +684,14 @@ def main():
         checks.append({"what": "C5 samples (all ranks)", "ok": multi["c5"]["parity_ok"]})
 
     # ---- north-star point, driver-run when the GPU's memory allows ---------
-    headline = None
+    headline = c3 = None
     if world == 1 and not args.no_headline and N == N_RAYS:
         headline = leg_headline(eng, exact)
         if "parity" in headline:
             checks.append(headline["parity"])
+        c3 = leg_c3(eng)
+        if "parity" in c3:
+            checks.append(c3["parity"])
 
     # ---- CPU baseline: the reference itself on the host cores ---------------
     cpu = None
@@ -678,7 +726,7 @@ def main():
                          "kernel": "rtx::trace_kernel<double>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks, "headline": headline, "multi_gpu": multi,
+            "clocks": clocks, "headline": headline, "c3": c3, "multi_gpu": multi,
             "parity_checks": checks,
         }))
     if dist is not None:
