@@ -274,7 +274,10 @@ def leg_c3(eng):
     got = np.stack([eng.download_rays(out[0].rows(j), idx) for j in range(S)]).astype(np.float64)
     flips = np.isnan(got) != np.isnan(want)         # rays within FP32 of an aperture edge
     both = ~np.isnan(got) & ~np.isnan(want)
-    err = float(np.max(np.abs(got - want)[both]/np.maximum(np.abs(want[both]), 1.0)))
+    # SURVEY 8d comparator: per-surface scale for lengths (as tests/test_gpu_parity.py)
+    scale = np.maximum(np.nanmax(np.abs(want), axis=(1, 2), keepdims=True), 1.0)
+    rel = np.abs(got - want)/np.maximum(np.abs(want), scale)
+    err = float(np.max(rel[both]))
     par = {"what": "C3 FP32 y sample of %d rays vs the FP64 oracle" % len(idx),
            "max_rel_err": err, "nan_mask_flips": int(flips.sum()), "entries": int(flips.size),
            "ok": bool(err <= 1e-5 and flips.mean() < 5e-3)}
