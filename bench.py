@@ -515,12 +515,26 @@ def main():
     # ---- device-resident workload: 3 bundles, 3 full result sets ----------
     host_rays = []
     dev = []
+    # the launch rays are GENERATED IN HBM (rtx_aim_rays: pupil coordinates uniform
+    # in the unit disc from the counter-based generator, seed per rank and
+    # wavelength; InfiniteConjugate.aim from the reference's stored pupil-aiming
+    # solution z, p); the e2e legs need them in page-locked host memory: one
+    # D2H of the generated bundles before anything is timed
+    import types
+    from rayopt_b200.rays import GRID_RANDOM, aim_record
+    obj = types.SimpleNamespace(finite=False, angle=ent["object_angle"], projection="rectilinear",
+                                pupil=types.SimpleNamespace(telecentric=False))
     for li in range(nl):
-        y0, u0 = make_rays(ent, li, N, seed=1000*rank + li)
-        py, pu = eng.pinned_empty(y0.shape), eng.pinned_empty(u0.shape)
-        py[:], pu[:] = y0, u0
+        aim = ent["aim"][li][FIELD_INDEX]
+        spec = aim_record(obj, aim["field"], aim["z"], aim["p"], dict(grid=GRID_RANDOM, n=N - 1),
+                          False, None, seed=1000*rank + li)
+        y0, u0 = eng.aim_rays(spec)                     # N - 1 random rays + the chief ray
+        assert y0.shape[0] == N
+        py, pu = eng.pinned_empty((N, 3)), eng.pinned_empty((N, 3))
+        y0.download(out=py)
+        u0.download(out=pu)
         host_rays.append((py, pu))
-        d = {"y0": eng.to_device(py), "u0": eng.to_device(pu),
+        d = {"y0": y0, "u0": u0,
              "Y": eng.empty((S, ld, 3)), "U": eng.empty((S, ld, 3)),
              "I": eng.empty((S, ld, 3)), "T": eng.empty((S, ld))}
         dev.append(d)
@@ -718,6 +732,8 @@ def main():
                        "stores": "direct" if args.direct else "tma-bulk",
                        "kernel_config": "rpt=%s store=%s warps=%s nbuf=%s (0/unset: library default rpt 2, per-CTA TMA bulk stores, 16 warps, 1 staging buffer)" % (args.rpt, os.environ.get("RTX_STORE", "-"), os.environ.get("RTX_WARPS", "-"), os.environ.get("RTX_NBUF", "-")),
                        "numa_node": node,
+                       "rays": "aimed bundles generated in HBM (rtx_aim_rays, random disc, seed per "
+                               "rank and wavelength)",
                        "l2": "outputs %.1f GB per launch >> 126 MB L2 (no flush needed)"
                              % (alg_bytes/1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
