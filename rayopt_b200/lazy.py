@@ -303,7 +303,8 @@ class ResidentMixin:
         resident intercepts (moment passes on the device, 64 bytes back)."""
         eng = self._engine()
         i = range(self.length)[i]
-        ref_point = None if ref is None else self.y[i][ref, :2]
+        ref_point = None if ref is None else \
+            eng.download_rays(self._dev["y"].rows(i), [int(ref)])[0, :2]    # 24 bytes, not the row
         return eng.rms(self._dev["y"].rows(i), self._weights(), N=self.nrays,
                        ref_point=ref_point)
 

@@ -305,6 +305,9 @@ class FakeResidentEngine:
     def sync(self):
         pass
 
+    def download_rays(self, d, idx):
+        return d.a.reshape(-1, 3)[np.asarray(idx)].copy()
+
     def rms(self, y, w, N=None, ref_point=None):
         yy = y.a[0, :N, :2]
         c = yy.mean(0) if ref_point is None else np.asarray(ref_point)
