@@ -388,6 +388,11 @@ def test_bound_resident_class_matches_reference():
     # device epilogue is exercised on the GPU, tests/test_gpu_dropin_reference.py)
     for a, b in zip(R.GeometricTrace.opd(got, resample=False), ref.opd(resample=False)):
         np.testing.assert_allclose(a, b, rtol=0, atol=1e-9)
+    # the reference's report methods read the LazyRows like arrays
+    small_r, small_g = R.GeometricTrace(s1), GT(s2)
+    for t in (small_r, small_g):
+        t.rays_point((0, .7), nrays=7, distribution="meridional")
+    assert str(small_g) == str(small_r)
     # item assignment writes through (the reference's own rays_given would use it)
     got.y[0, :, 1] = 7.
     assert np.all(got.y[0][:, 1] == 7.) and np.all(got._dev["y"].a[0, :got.nrays, 1] == 7.)

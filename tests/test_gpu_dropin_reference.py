@@ -181,6 +181,23 @@ def test_fused_reduce_large_bundle(R, eng):
     got.free()
 
 
+@pytest.mark.parametrize("resident", [False, True])
+def test_text_and_resize_of_the_reference_class(R, eng, resident):
+    """the reference's report / housekeeping methods run unchanged on the bound
+    class: ``str(trace)`` (print_trace: cumsum of t, per-ray rows,
+    geometric_trace.py:241-259) and ``resize`` (:231-234)"""
+    from rayopt_b200 import bind
+    s1, s2 = build(R, "cooke"), build(R, "cooke")
+    ref = R.GeometricTrace(s1)
+    got = bind(R.GeometricTrace, engine=eng, exact=True, resident=resident)(s2)
+    for t in (ref, got):
+        t.rays_point((0, .7), nrays=7, distribution="meridional")
+    assert str(got) == str(ref) and len(str(ref)) > 500
+    ref.resize(fn=lambda a, b: a)
+    got.resize(fn=lambda a, b: a)
+    assert [e.radius for e in s1[1:]] == [e.radius for e in s2[1:]]
+
+
 def test_analysis_consumers_read_single_rows(R, eng):
     """what Analysis.transverse / spots read (analysis.py:231-245,269-280) from
     a resident bound trace: only the rows asked for cross PCIe"""
