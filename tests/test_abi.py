@@ -34,6 +34,10 @@ def test_header_symbols_all_exported(lib):
 def test_abi_version_and_layout(lib):
     assert lib.rtx_abi_version() == 2
     assert lib.rtx_sizeof_surface() == SURFACE_DTYPE.itemsize
+    from rayopt_b200.engine import OPD_DTYPE
+    from rayopt_b200.rays import aim_dtype
+    assert lib.rtx_sizeof_opd() == OPD_DTYPE.itemsize       # struct rtx_opd
+    assert lib.rtx_sizeof_aim() == aim_dtype().itemsize     # struct rtx_aim
 
 
 def test_strerror(lib):
@@ -74,3 +78,20 @@ def test_no_cpu_fallback():
     from rayopt_b200.engine import Engine
     with pytest.raises(_lib.RtxError):
         Engine(0)
+
+
+def test_cpu_reference_arm_harness():
+    """oracle/cpu_bench.py (the bench's reference arm): persistent worker
+    processes, whole-workload sharding, both kinds -- a tiny run on two
+    processes returns a consistent record"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_bench
+    kinds = ["port"] + (["reference"] if cpu_bench.reference_available() else [])
+    for kind in kinds:
+        r = cpu_bench.run("double_gauss", (0., .7), procs=2, steps=2, warmup=2, kind=kind,
+                          rays_total=4001, warm_rays=100)
+        assert r["kind"] == kind and r["cores"] == 2 and r["rays_per_proc"] == 2001
+        assert r["surfaces"] == 12 and r["wavelengths"] == 3 and len(r["seconds"]) == 2
+        assert r["ray_surfaces_per_step"] == 2*2001*3*12
+        assert abs(r["value"] - r["ray_surfaces_per_step"]*2/sum(r["seconds"])) < 1e-6*r["value"]
