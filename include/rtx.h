@@ -260,9 +260,17 @@ int rtx_set_path_sum_output(rtx_ctx *ctx, void *dsum, int upto);
 /*
  * Same call with HOST buffers in the reference layout: y0,u0 (N,3);
  * Y,U,I (rows,N,3), T (rows,N) C-contiguous (GeometricTrace.y/u/i/t rows
- * start..stop-1).  Rays are processed in chunks; H2D, kernel and D2H of
- * consecutive chunks overlap on three streams.  Host buffers from
- * rtx_host_alloc (pinned) copy at full PCIe rate; pageable ones work too.
+ * start..stop-1).  Synchronous.  Three regimes by size (rays + results):
+ *   <= 16 KB  (ray aiming: 1-3 rays, hundreds of calls, rayopt/system.py:
+ *             507-555) ZERO-COPY: the kernel reads the rays from and writes
+ *             the results to a page-locked bounce buffer over PCIe -- one
+ *             launch, one synchronisation;
+ *   <= 4 MB   one H2D, one launch, one D2H through the bounce buffer;
+ *   larger    rays are processed in ~256 MB chunks; H2D, kernel and D2H of
+ *             consecutive chunks overlap on two streams.  Host buffers from
+ *             rtx_host_alloc (pinned) copy at full PCIe rate; pageable ones
+ *             work too.
+ * The mask / path-sum side outputs do not apply to host-buffer calls.
  */
 int rtx_trace_host(rtx_ctx *ctx, const rtx_surface *surf, int S,
                    const double *rot0, int dtype, int64_t N,
