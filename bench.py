@@ -611,14 +611,49 @@ def main():
     # one buffer (i[j] == u[j-1] bit for bit) and moves 56 B per ray-surface;
     # "full_copy" is the same through rtx_trace_host with all four arrays
     # (80 B per ray-surface).
-    def timed(fn, steps):
+    per_rank = {}
+
+    def timed(fn, steps, tag=None):
         fn()
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        own = time.perf_counter() - t0               # this rank's own work, before the barrier
         barrier()
-        return maxr(time.perf_counter() - t0)
+        dt = maxr(time.perf_counter() - t0)
+        if tag and dist is not None:                 # who is the slow one? (ms per step, by rank)
+            t = torch.zeros(world, device="cuda", dtype=torch.float64)
+            t[rank] = own/steps*1e3
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            per_rank[tag] = [round(float(x), 1) for x in t.cpu()]
+        return dt
+
+    def pcie_probe():
+        """all ranks at once: one 1 GiB D2H and one 1 GiB H2D between HBM and this
+        rank's page-locked (NUMA-local) memory, GB/s per rank -- the ceiling the
+        host side leaves to the e2e pipeline when every GPU of the box copies"""
+        from rayopt_b200._lib import check, ptr
+        nb = 1 << 30
+        h, d = eng.pinned_empty((nb,), np.uint8), eng.empty((nb,), np.uint8)
+        out = {}
+        for name, fn in (("d2h", lambda: check(eng.lib.rtx_memcpy_d2h(eng.ctx, ptr(h), d.ptr, nb))),
+                         ("h2d", lambda: check(eng.lib.rtx_memcpy_h2d(eng.ctx, d.ptr, ptr(h), nb)))):
+            fn()
+            eng.sync()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn()
+            eng.sync()
+            gbs = 3*nb/(time.perf_counter() - t0)/1e9
+            t = torch.zeros(world, device="cuda", dtype=torch.float64)
+            t[rank] = gbs
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            out[name + "_GBps_per_rank"] = [round(float(x), 1) for x in t.cpu()]
+            barrier()
+        d.free()
+        return out
 
     e2e = None
     if not args.no_e2e:
@@ -635,7 +670,7 @@ def main():
                 g.l = l
                 g.propagate(clip=True)
         e2e_steps = max(1, min(args.steps, 3))
-        dt = timed(e2e_step, e2e_steps)
+        dt = timed(e2e_step, e2e_steps, "e2e")
         # what came back to the host (last wavelength traced)
         wl = np_oracle.trace(ent["tables"][nl - 1], host_rays[0][0][idx], host_rays[0][1][idx],
                              clip=True)
@@ -647,6 +682,9 @@ def main():
                "steps": e2e_steps, "ms_per_step": dt/e2e_steps*1e3,
                "api": "GeometricTrace.propagate(clip=True) -> rtx_trace_host: pinned host arrays, "
                       "chunked H2D/kernel/D2H pipeline; y,u,t copied back, i is a view of u"}
+        if dist is not None:
+            e2e["ms_per_step_by_rank"] = per_rank.get("e2e")
+            e2e["pcie_probe_all_ranks_at_once"] = pcie_probe()
         del g
         import gc
         gc.collect()
