@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """three wavelength bundles (C2): 3 launches vs one batched launch"""
-import os, statistics, sys
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench

@@ -407,7 +407,6 @@ def test_resident_rays_point_matches_reference():
     warnings.simplefilter("ignore")
     R = ref_shim.load()
     from rayopt_b200 import ResidentTrace
-    from rayopt_b200.rays import hexapolar
 
     import aim_oracle
 
