@@ -200,9 +200,10 @@ int launch_cfg(rtx_ctx* ctx, const TraceParams<T>& p, int rpt, int store, int wa
     RTX_CASE(1, STORE_CTA, 16, 1)
     RTX_CASE(2, STORE_CTA, 32, 1)
     RTX_CASE(2, STORE_CTA, 8, 1)
+    RTX_CASE(2, STORE_WARP, 16, 2)
     if constexpr (sizeof(T) == 4) {  // FP32: four rays per thread (64 registers leave room)
         RTX_CASE(4, STORE_CTA, 16, 1)
-        RTX_CASE(4, STORE_WARP, 8, 2)
+        RTX_CASE(4, STORE_WARP, 16, 1)
     }
 #ifdef RTX_TUNING_SPACE
     RTX_CASE(2, STORE_CTA, 8, 2)
@@ -219,8 +220,11 @@ int launch_cfg(rtx_ctx* ctx, const TraceParams<T>& p, int rpt, int store, int wa
         RTX_CASE(4, STORE_CTA, 8, 1)
         RTX_CASE(4, STORE_CTA, 32, 1)
     }
-    RTX_CASE(2, STORE_WARP, 16, 2)
     RTX_CASE(2, STORE_WARP, 16, 1)
+    if constexpr (sizeof(T) == 4) {
+        RTX_CASE(4, STORE_WARP, 16, 2)
+        RTX_CASE(4, STORE_WARP, 8, 2)
+    }
 #endif
 #undef RTX_CASE
     return RTX_E_UNSUPPORTED;
@@ -372,9 +376,10 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
         //  FP32: 4 rays/thread x 16 warps (2048-ray tiles, 24 KB runs again):
         //        half the per-thread overhead instructions of 2 rays/thread     0.92-0.94
         //  systems with >= 25 % Newton (aspheric) surfaces are bound by issue
-        //  slots / the FP64 pipe, not by HBM: small 8-warp CTAs (3 resident
-        //  CTAs per SM) -- FP64: per-CTA stores in lockstep 0.87; FP32: 4 rays
-        //  per thread, free-running warps with per-warp stores 0.85
+        //  slots / the FP64 pipe, not by HBM: free-running 16-warp CTAs with
+        //  per-warp stores (no lockstep barrier behind the long, divergent
+        //  Newton chains) -- FP64 0.88, FP32 (4 rays per thread) 0.88
+        //  (profiles/r2l_sweep_heavy_configs.txt)
         int newton = 0;
         for (int i = 0; i < S; ++i) newton += surf && surf[i].n_asph >= 0;
         heavy = newton * 4 >= S;
@@ -382,23 +387,22 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
             rpt = 4;
             if (heavy) {
                 store = STORE_WARP;
-                warps = 8;
-                nbuf = 2;
+                warps = 16;
+                nbuf = 1;
             } else {
                 store = STORE_CTA;
                 warps = 16;
                 nbuf = 1;
             }
         } else if (heavy) {
+            // free-running warps with per-warp stores: 16-warp CTAs in fast mode
+            // (0.88; 8-warp CTAs with per-CTA stores 0.855 on the same box,
+            // profiles/r2l_sweep_heavy_configs.txt), 8-warp CTAs for the
+            // separately rounded Newton of RTX_EXACT (0.77)
             rpt = 2;
-            warps = 8;
-            if (exact) {  // the separately rounded Newton keeps the free-running kernel
-                store = STORE_WARP;
-                nbuf = 2;
-            } else {
-                store = STORE_CTA;
-                nbuf = 1;
-            }
+            store = STORE_WARP;
+            nbuf = 2;
+            warps = exact ? 8 : 16;
         }
     }
     if (N <= 32 * 1024) {  // small bundles: spread over more warps
