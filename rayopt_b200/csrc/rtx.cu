@@ -367,7 +367,6 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
     if (flags & RTX_RPT2) rpt = 2;
     int store = ctx->store, warps = ctx->warps, nbuf = ctx->nbuf;
     bool heavy = false;
-    const bool exact = (flags & RTX_EXACT) != 0;
     const bool explicit_rpt = (flags & (RTX_RPT1 | RTX_RPT2)) != 0;
     if (!ctx->tuned && !explicit_rpt) {
         // measured best configurations (profiles/r1_sweep8_defaults.txt,
@@ -395,14 +394,13 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
                 nbuf = 1;
             }
         } else if (heavy) {
-            // free-running warps with per-warp stores: 16-warp CTAs in fast mode
-            // (0.88; 8-warp CTAs with per-CTA stores 0.855 on the same box,
-            // profiles/r2l_sweep_heavy_configs.txt), 8-warp CTAs for the
-            // separately rounded Newton of RTX_EXACT (0.77)
+            // free-running 16-warp CTAs with per-warp stores (fast 0.88, RTX_EXACT
+            // 0.80; 8-warp CTAs: 0.855 with per-CTA stores / 0.77 exact on the
+            // same box, profiles/r2l_sweep_heavy_configs.txt)
             rpt = 2;
             store = STORE_WARP;
             nbuf = 2;
-            warps = exact ? 8 : 16;
+            warps = 16;
         }
     }
     if (N <= 32 * 1024) {  // small bundles: spread over more warps
