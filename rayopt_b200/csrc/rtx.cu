@@ -403,7 +403,30 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
             warps = 16;
         }
     }
-    if (N <= 32 * 1024) {  // small bundles: spread over more warps
+    if (N <= 150 * 1000 && !ctx->tuned) {
+        // small bundles: 256-ray warp tiles spread over all SMs (5e4 rays:
+        // 0.35 vs 0.24 with 1024-ray tiles, profiles/r2n_midsize_configs.txt)
+        rpt = 1;
+        store = STORE_WARP;
+        warps = 8;
+        nbuf = 2;
+    } else if (N <= 1500 * 1000 && !ctx->tuned && !explicit_rpt && !heavy && sizeof(T) == 8) {
+        // mid-size FP64 bundles (what an analysis traces): 512-ray tiles, two
+        // resident CTAs per SM -- twice the tiles to balance over the SMs
+        // (3e5 rays 0.78 -> 0.88, 1e6 rays 0.81 -> 0.88)
+        rpt = 1;
+        store = STORE_CTA;
+        warps = 16;
+        nbuf = 1;
+    } else if (N > 500 * 1000 && N <= 2500 * 1000 && !ctx->tuned && !explicit_rpt && !heavy &&
+               sizeof(T) == 4) {
+        // mid-size FP32 bundles: 512-ray tiles, three resident CTAs per SM
+        // (1e6 rays 0.72 -> 0.92, 2e6 rays 0.81 -> 0.83)
+        rpt = 2;
+        store = STORE_CTA;
+        warps = 8;
+        nbuf = 1;
+    } else if (N <= 32 * 1024) {  // (tuned contexts keep the old small-bundle rule)
         rpt = 1;
         store = STORE_WARP;
         warps = 8;
