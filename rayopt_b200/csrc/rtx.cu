@@ -381,7 +381,10 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
         //  (profiles/r2l_sweep_heavy_configs.txt)
         int newton = 0;
         for (int i = 0; i < S; ++i) newton += surf && surf[i].n_asph >= 0;
-        heavy = newton * 4 >= S;
+        // ... and so is a keep-LAST trace (one stored row: the stores are no
+        // limit): free-running CTAs, 1e7 rays x 12 surfaces 0.94 -> 0.84 ms
+        // (profiles/r2p_keep_last_configs.txt)
+        heavy = newton * 4 >= S || keep == RTX_KEEP_LAST;
         if (sizeof(T) == 4) {
             rpt = 4;
             if (heavy) {

@@ -20,6 +20,7 @@ ap.add_argument("--system", default="double_gauss")
 ap.add_argument("--dtype", default="f64")
 ap.add_argument("--device-rays", type=int, default=0,
                 help="1: hexapolar launch rays generated in HBM (large bundles)")
+ap.add_argument("--keep-last", type=int, default=0, help="1: store the last surface only (compute-bound)")
 ap.add_argument("--pad", type=int, default=0, help="extra rays of row pitch (ld = N rounded + pad)")
 ap.add_argument("--gap", type=int, default=0, help="bytes of dummy allocation between the result arrays")
 ap.add_argument("cfgs", nargs="*", default=["2,2,16,1,0,0,1"])
@@ -63,13 +64,13 @@ for cfg in a.cfgs:
     e = Engine(0)
     ms = []
     try:
-        e.trace_device(ent["tables"][0], d_y0, d_u0, Y, U, I, T, N=N, ld=ld, clip=True, exact=bool(a.exact))
+        e.trace_device(ent["tables"][0], d_y0, d_u0, Y, U, I, T, N=N, ld=ld, clip=True, exact=bool(a.exact), keep_last=bool(a.keep_last))
     except Exception as ex:
         print("cfg %s: %s" % (cfg, ex), flush=True)
         e.close()
         continue
     for i in range(12):
-        e.trace_device(ent["tables"][0], d_y0, d_u0, Y, U, I, T, N=N, ld=ld, clip=True, exact=bool(a.exact))
+        e.trace_device(ent["tables"][0], d_y0, d_u0, Y, U, I, T, N=N, ld=ld, clip=True, exact=bool(a.exact), keep_last=bool(a.keep_last))
         t = e.last_kernel_ms()
         if i >= 4:
             ms.append(t)
