@@ -384,7 +384,8 @@ int trace_device(rtx_ctx* ctx, const rtx_surface* surf, int S, const double* rot
         // ... and so is a keep-LAST trace (one stored row: the stores are no
         // limit): free-running CTAs, 1e7 rays x 12 surfaces 0.94 -> 0.84 ms
         // (profiles/r2p_keep_last_configs.txt)
-        heavy = newton * 4 >= S || keep == RTX_KEEP_LAST;
+        // (a fused gather keeps the per-CTA 24 KB runs for its NVLink stores)
+        heavy = newton * 4 >= S || (keep == RTX_KEEP_LAST && !(peers && peers->n > 0));
         if (sizeof(T) == 4) {
             rpt = 4;
             if (heavy) {
